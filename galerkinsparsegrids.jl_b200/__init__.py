@@ -1,0 +1,532 @@
+"""gsg_b200 -- host-side mirror of GalerkinSparseGrids.jl's operator API over libgsgb200.so.
+
+Julia is not available in this image, so the host side above the C ABI (include/gsg_b200.h) is
+written in Python and mirrors the reference's names, argument meaning and error behaviour for
+the hot path: `get_size`, `V2D`/`D2V`, `cell_index`, `periodic_DLF_matrix`, `D_matrix`,
+`grad_matrix`, `laplacian_matrix`, `tensor_construct`, `reconstruct_DG`, `mcerr`,
+`wave_evolve`, `energy_func` (reference: src/GalerkinSparseGrids.jl:32-71).  All arithmetic on
+the path runs in the CUDA library; there is no CPU fallback and nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from typing import Sequence
+
+import numpy as np
+
+from ._lib import GsgError, LIB_PATH, SIGNATURES, check, lib
+
+__all__ = [
+    "GsgError", "Plan", "get_plan", "get_size", "cell_index", "basis_v", "basis_tables",
+    "periodic_DLF_matrix", "coeffs_DG", "vcoeffs_DG", "tensor_construct", "V2D", "D2V", "V2Dref",
+    "D2Vref", "D_matrix", "grad_matrix", "laplacian_matrix", "reconstruct_DG", "mcerr",
+    "wave_evolve", "advect_evolve", "energy_func", "spmv_csc", "CsrMatrix", "device_info",
+    "launch_count",
+]
+
+_SCHEME = {"sparse": 0, "full": 1}
+
+
+def _scheme(scheme: str) -> int:
+    try:
+        return _SCHEME[scheme]
+    except KeyError:
+        raise ValueError(f"ArgumentError: scheme={scheme!r}") from None
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _devptr(t) -> C.c_void_p:
+    """Device pointer of a torch tensor / anything with data_ptr(), or a raw int."""
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(int(t))
+
+
+# ---------------------------------------------------------------------------------------------
+# setup mirrors (CPU side of the library)
+# ---------------------------------------------------------------------------------------------
+def launch_count() -> int:
+    return int(lib.gsg_launch_count())
+
+
+def device_info(device: int = 0) -> dict:
+    buf = C.create_string_buffer(256)
+    check(lib.gsg_device_info(device, buf, 256))
+    name, sms, cc, mem = buf.value.decode().split(";")
+    return {"name": name, "sm_count": int(sms), "cc": cc, "global_mem": int(mem)}
+
+
+def get_size(D: int, k: int, n: int, scheme: str = "sparse") -> int:
+    """get_size(Val(D), k, n, Val(scheme)) -- src/dg_vmethods.jl:35-45."""
+    out = C.c_int64()
+    check(lib.gsg_get_size(D, k, n, _scheme(scheme), C.byref(out)))
+    return out.value
+
+
+def cell_index(x: float, l: int) -> int:
+    """cell_index(x, l) -- src/dg_methods.jl:70-79 (0-based level, 1-based cell)."""
+    out = C.c_int64()
+    check(lib.gsg_cell_index(float(x), int(l), C.byref(out)))
+    return out.value
+
+
+def basis_v(k: int, level: int, cell: int, mode: int, x) -> np.ndarray:
+    """v(k, level, cell, mode, x) -- src/dg_methods.jl:27-36, vectorised over x."""
+    x = _f64(np.atleast_1d(x))
+    out = np.empty_like(x)
+    check(lib.gsg_basis_v(k, level, cell, mode, _ptr(x), x.size, _ptr(out)))
+    return out
+
+
+def basis_tables(k: int):
+    """(leg_coeffs, dg_coeffs[k]) -- src/1d_dg_functions.jl:35,52-62."""
+    leg = np.empty((11, 22))
+    dg = np.empty((k, 2 * k))
+    check(lib.gsg_basis_tables(k, _ptr(leg), _ptr(dg)))
+    return leg, dg
+
+
+_H_CACHE: dict = {}
+
+
+def periodic_DLF_matrix(k: int, max_level: int, basis: str = "hier"):
+    """periodic_DLF_matrix(k, n; basis) -- src/1d_derivative.jl:136-148.  Returns a
+    scipy.sparse.csc_matrix (0-based); the "nodal"/"point" variants are broken in the
+    reference (they call the undefined modal2points_1D) and raise here too."""
+    import scipy.sparse as sp
+    if basis not in ("hier", "pos"):
+        raise ValueError(f"ArgumentError: basis={basis!r}")
+    key = (k, max_level, basis)
+    if key not in _H_CACHE:
+        b = 0 if basis == "hier" else 1
+        nnz = C.c_int64(0)
+        check(lib.gsg_dlf_matrix(k, max_level, b, C.byref(nnz), None, None, None))
+        N = k << max_level
+        colptr = np.empty(N + 1, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        nzval = np.empty(nnz.value, dtype=np.float64)
+        check(lib.gsg_dlf_matrix(k, max_level, b, C.byref(nnz), _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+        _H_CACHE[key] = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(N, N))
+    return _H_CACHE[key]
+
+
+def _hier_index_list(k: int, n: int):
+    for level in range(n + 1):
+        for cell in range(1, (1 << max(0, level - 1)) + 1):
+            for mode in range(1, k + 1):
+                yield level, cell, mode
+
+
+def vcoeffs_DG(D: int, k: int, n: int, f, scheme: str = "sparse", npts: int = 20) -> np.ndarray:
+    """vcoeffs_DG(1, k, n, f) -- src/dg_vmethods.jl:149-179, 1-D only: the projection of
+    arbitrary D-dimensional closures by adaptive cubature stays on the host language side
+    (SURVEY.md section 2); product inputs for D > 1 come from tensor_construct, as in the
+    reference's own examples (examples/traveling_wave.jl:18-48)."""
+    if D != 1:
+        raise NotImplementedError("vcoeffs_DG: only D == 1; use tensor_construct for D > 1")
+    xs, ws = np.polynomial.legendre.leggauss(npts)
+    out = np.empty(k << n)
+    for j, (level, cell, mode) in enumerate(_hier_index_list(k, n)):
+        w = 1 << max(0, level - 1)
+        a, b = (cell - 1) / w, cell / w
+        mid = 0.5 * (a + b)
+        tot = 0.0
+        for lo, hi in ((a, mid), (mid, b)):
+            half, c = 0.5 * (hi - lo), 0.5 * (hi + lo)
+            x = c + half * xs
+            fx = np.array([f(float(xi)) for xi in x], dtype=np.float64)
+            tot += half * float(np.dot(ws, fx * basis_v(k, level, cell, mode, x)))
+        out[j] = tot
+    return out
+
+
+def coeffs_DG(D: int, k: int, n: int, f, scheme: str = "sparse"):
+    """coeffs_DG(1, k, n, f) -- src/dg_methods.jl:113-143, as a dict (see V2D)."""
+    return V2D(D, k, n, vcoeffs_DG(D, k, n, f, scheme=scheme), scheme=scheme)
+
+
+def tensor_construct(D: int, k: int, n: int, vcoeff_array: Sequence, scheme: str = "sparse") -> np.ndarray:
+    """tensor_construct(D, k, n, [v_1..v_D]; scheme), vector overload --
+    src/tensor_construct.jl:57-63."""
+    if len(vcoeff_array) != D:
+        raise ValueError("tensor_construct: need D coefficient vectors")
+    vs = [_f64(v) for v in vcoeff_array]
+    for v in vs:
+        if v.size != (k << n):
+            raise ValueError("tensor_construct: 1-D vectors must have length k*2^n")
+    arr = (C.c_void_p * D)(*[v.ctypes.data for v in vs])
+    out = np.empty(get_size(D, k, n, scheme))
+    check(lib.gsg_tensor_construct(D, k, n, _scheme(scheme), arr, _ptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# vector <-> dict layout (pure permutations; src/dg_vmethods.jl:48-142)
+# ---------------------------------------------------------------------------------------------
+def _levels(D: int, n: int, scheme: str):
+    full = _scheme(scheme) == 1
+    for rev in itertools.product(range(1, n + 2), repeat=D):
+        level = rev[::-1]                      # first index fastest
+        if not full and sum(level) > n + D:    # src/schemes.jl:21-23
+            continue
+        yield level
+
+
+def V2D(D: int, k: int, n: int, vect, scheme: str = "sparse") -> dict:
+    """V2D -- src/dg_vmethods.jl:76-100.  dict: 1-based level tuple -> ndarray indexed
+    [m_1..m_D, c_1..c_D] (0-based), i.e. the block exactly as it sits in the vector."""
+    vect = np.asarray(vect)
+    out, j = {}, 0
+    for level in _levels(D, n, scheme):
+        cells = tuple(1 << max(0, l - 2) for l in level)
+        size = int(np.prod(cells)) * k ** D
+        out[level] = vect[j:j + size].reshape((k,) * D + cells, order="F").copy()
+        j += size
+    if j != vect.size:
+        raise ValueError("V2D: vector length does not match get_size")
+    return out
+
+
+def D2V(D: int, k: int, n: int, coeffs: dict, scheme: str = "sparse") -> np.ndarray:
+    """D2V -- src/dg_vmethods.jl:48-73."""
+    parts = [np.asarray(coeffs[level]).reshape(-1, order="F") for level in _levels(D, n, scheme)]
+    return np.concatenate(parts) if parts else np.empty(0)
+
+
+def V2Dref(D: int, k: int, n: int, scheme: str = "sparse"):
+    """V2Dref -- src/dg_vmethods.jl:123-142: list of 1-based (level, cell, mode) tuples."""
+    out = []
+    for level in _levels(D, n, scheme):
+        cells = tuple(1 << max(0, l - 2) for l in level)
+        for crev in itertools.product(*[range(1, c + 1) for c in cells[::-1]]):
+            for mrev in itertools.product(range(1, k + 1), repeat=D):
+                out.append((level, crev[::-1], mrev[::-1]))
+    return out
+
+
+def D2Vref(D: int, k: int, n: int, scheme: str = "sparse") -> dict:
+    """D2Vref -- src/dg_vmethods.jl:102-121 (1-based indices)."""
+    return {lcm: j + 1 for j, lcm in enumerate(V2Dref(D, k, n, scheme))}
+
+
+# ---------------------------------------------------------------------------------------------
+# plan + operators
+# ---------------------------------------------------------------------------------------------
+class Plan:
+    """Device-resident operator plan for (D, k, n, scheme).  Replaces the assembled
+    SparseMatrixCSC of grad_matrix / laplacian_matrix (src/multidim_derivative.jl:61-79)."""
+
+    def __init__(self, D: int, k: int, n: int, scheme: str = "sparse", H=None, device: int = 0):
+        import scipy.sparse as sp
+        self.D, self.k, self.n, self.scheme = D, k, n, scheme
+        if H is None:
+            H = periodic_DLF_matrix(k, n)
+        H = sp.csc_matrix(H)
+        H.sort_indices()
+        colptr = (H.indptr.astype(np.int64) + 1)
+        rowval = (H.indices.astype(np.int64) + 1)
+        nzval = _f64(H.data)
+        handle = C.c_void_p()
+        check(lib.gsg_plan_create(D, k, n, _scheme(scheme), H.shape[0], _ptr(colptr), _ptr(rowval),
+                                  _ptr(nzval), device, C.byref(handle)))
+        self._h = handle
+        size = C.c_int64()
+        check(lib.gsg_plan_size(self._h, C.byref(size)))
+        self.size = size.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.gsg_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host vectors ----------------------------------------------------------------------
+    def _vec(self, x) -> np.ndarray:
+        x = _f64(x)
+        if x.shape != (self.size,):
+            raise ValueError(f"DimensionMismatch: expected length {self.size}, got {x.shape}")
+        return x
+
+    def apply_D(self, d: int, x) -> np.ndarray:
+        x = self._vec(x)
+        y = np.empty_like(x)
+        check(lib.gsg_apply_D(self._h, d, _ptr(x), _ptr(y)))
+        return y
+
+    def apply_grad(self, a, x) -> np.ndarray:
+        x = self._vec(x)
+        a = _f64(a)
+        if a.size != self.D:
+            raise ValueError("apply_grad: need D coefficients")
+        y = np.empty_like(x)
+        check(lib.gsg_apply_grad(self._h, _ptr(a), _ptr(x), _ptr(y)))
+        return y
+
+    def apply_laplacian(self, x) -> np.ndarray:
+        x = self._vec(x)
+        y = np.empty_like(x)
+        check(lib.gsg_apply_laplacian(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def rk4_advect(self, a, y, dt: float, nsteps: int) -> np.ndarray:
+        y = self._vec(y).copy()
+        a = _f64(a)
+        check(lib.gsg_rk4_advect(self._h, _ptr(a), _ptr(y), float(dt), int(nsteps)))
+        return y
+
+    def rk4_wave(self, u, v, dt: float, nsteps: int):
+        u = self._vec(u).copy()
+        v = self._vec(v).copy()
+        check(lib.gsg_rk4_wave(self._h, _ptr(u), _ptr(v), float(dt), int(nsteps)))
+        return u, v
+
+    def energy(self, u, udot) -> float:
+        u, udot = self._vec(u), self._vec(udot)
+        out = C.c_double()
+        check(lib.gsg_energy(self._h, _ptr(u), _ptr(udot), C.byref(out)))
+        return out.value
+
+    def reconstruct(self, vcoeffs, points) -> np.ndarray:
+        """points: (npts, D) array (row i = point i; same memory as Julia's D x npts)."""
+        vcoeffs = self._vec(vcoeffs)
+        pts = _f64(points).reshape(-1, self.D)
+        out = np.empty(pts.shape[0])
+        check(lib.gsg_reconstruct(self._h, _ptr(vcoeffs), _ptr(pts), pts.shape[0], _ptr(out)))
+        return out
+
+    # -- device vectors (torch tensors or raw pointers) ------------------------------------
+    def set_stream(self, stream) -> None:
+        s = getattr(stream, "cuda_stream", stream)
+        check(lib.gsg_plan_set_stream(self._h, C.c_void_p(int(s) if s else 0)))
+
+    def sync(self) -> None:
+        check(lib.gsg_plan_sync(self._h))
+
+    def apply_D_dev(self, d: int, x, y, alpha: float = 1.0, beta: float = 0.0) -> None:
+        check(lib.gsg_apply_D_dev(self._h, d, alpha, _devptr(x), beta, _devptr(y)))
+
+    def apply_grad_dev(self, a, x, y) -> None:
+        a = _f64(a)
+        check(lib.gsg_apply_grad_dev(self._h, _ptr(a), _devptr(x), _devptr(y)))
+
+    def apply_laplacian_dev(self, x, y, tmp) -> None:
+        check(lib.gsg_apply_laplacian_dev(self._h, _devptr(x), _devptr(y), _devptr(tmp)))
+
+    def rk4_advect_dev(self, a, y, dt: float, nsteps: int) -> None:
+        a = _f64(a)
+        check(lib.gsg_rk4_advect_dev(self._h, _ptr(a), _devptr(y), float(dt), int(nsteps)))
+
+    def rk4_wave_dev(self, u, v, dt: float, nsteps: int) -> None:
+        check(lib.gsg_rk4_wave_dev(self._h, _devptr(u), _devptr(v), float(dt), int(nsteps)))
+
+    def reconstruct_dev(self, vcoeffs, points, npts: int, out) -> None:
+        check(lib.gsg_reconstruct_dev(self._h, _devptr(vcoeffs), _devptr(points), int(npts), _devptr(out)))
+
+
+_PLANS: dict = {}
+
+
+def get_plan(D: int, k: int, n: int, scheme: str = "sparse") -> Plan:
+    key = (D, k, n, scheme)
+    if key not in _PLANS:
+        _PLANS[key] = Plan(D, k, n, scheme)
+    return _PLANS[key]
+
+
+class _Operator:
+    """What `D_matrix(...)` returns: supports `A * x` and `A @ x` like a SparseMatrixCSC."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        self.shape = (plan.size, plan.size)
+
+    def __mul__(self, x):
+        return self.matvec(x)
+
+    __matmul__ = __mul__
+
+
+class DOperator(_Operator):
+    def __init__(self, plan: Plan, d: int):
+        super().__init__(plan)
+        if not 1 <= d <= plan.D:
+            raise ValueError("BoundsError: axis d out of range")
+        self.d = d
+
+    def matvec(self, x):
+        return self.plan.apply_D(self.d, x)
+
+
+class LaplacianOperator(_Operator):
+    def matvec(self, x):
+        return self.plan.apply_laplacian(x)
+
+
+def D_matrix(D: int, d: int, k: int, n: int, scheme: str = "sparse") -> DOperator:
+    """D_matrix(D, d, k, n; scheme) -- src/multidim_derivative.jl:61-65 (matrix-free)."""
+    return DOperator(get_plan(D, k, n, scheme), d)
+
+
+def grad_matrix(D: int, k: int, n: int, scheme: str = "sparse"):
+    """grad_matrix -- src/multidim_derivative.jl:67-69."""
+    return [D_matrix(D, d, k, n, scheme) for d in range(1, D + 1)]
+
+
+def laplacian_matrix(D: int, k: int, n: int, scheme: str = "sparse") -> LaplacianOperator:
+    """laplacian_matrix -- src/multidim_derivative.jl:71-79 (applied as sum_d D_d(D_d x))."""
+    return LaplacianOperator(get_plan(D, k, n, scheme))
+
+
+# ---------------------------------------------------------------------------------------------
+# reconstruction and error measurement
+# ---------------------------------------------------------------------------------------------
+def reconstruct_DG(coeffs, xs, D: int | None = None, k: int | None = None, n: int | None = None,
+                   scheme: str = "sparse"):
+    """reconstruct_DG(coeffs, xs) -- src/dg_methods.jl:150-165, batched.  `coeffs` is either
+    the dict V2D returns (D, k, n inferred) or a vector with D, k, n given; `xs` is one
+    point (length D) or an (npts, D) array.  Returns a float or an array."""
+    if isinstance(coeffs, dict):
+        first_level = next(iter(coeffs))
+        D = len(first_level)
+        k = np.asarray(coeffs[first_level]).shape[0]
+        nlev = len(coeffs)
+        n = max(max(l) for l in coeffs) - 1
+        if scheme == "sparse" and nlev != math.comb(n + D, D):
+            scheme = "full"
+        vect = D2V(D, k, n, coeffs, scheme=scheme)
+    else:
+        if D is None or k is None or n is None:
+            raise ValueError("reconstruct_DG: D, k, n required with a coefficient vector")
+        vect = coeffs
+    pts = _f64(xs)
+    single = pts.ndim == 1 and pts.size == D
+    out = get_plan(D, k, n, scheme).reconstruct(vect, pts.reshape(-1, D))
+    return float(out[0]) if single else out
+
+
+def mcerr(coeffs, g, D: int, k: int, n: int, count: int = 1000, scheme: str = "sparse", rng=None) -> float:
+    """mcerr(x -> reconstruct_DG(dict, x), g, D; count) -- src/error_measure.jl:12-19,39-41:
+    sqrt(mean over `count` uniform points of (f - g)^2), with f evaluated in one batch."""
+    rng = np.random.default_rng() if rng is None else rng
+    pts = rng.random((count, D))
+    f = reconstruct_DG(coeffs, pts, D, k, n, scheme) if not isinstance(coeffs, dict) else reconstruct_DG(coeffs, pts)
+    gv = np.array([g(p) for p in pts])
+    return float(np.sqrt(np.mean((f - gv) ** 2)))
+
+
+# ---------------------------------------------------------------------------------------------
+# PDE drivers (src/pdes.jl)
+# ---------------------------------------------------------------------------------------------
+def _steps(time0: float, time1: float, dt: float):
+    nsteps = max(1, int(math.ceil((time1 - time0) / dt - 1e-12)))
+    return nsteps, (time1 - time0) / nsteps
+
+
+def wave_evolve(D: int, k: int, n: int, f0coeffs, v0coeffs, time0: float, time1: float,
+                order: str = "4", scheme: str = "sparse", dt: float | None = None, nout: int = 2):
+    """wave_evolve(D, k, n, f0coeffs, v0coeffs, t0, t1; order, scheme) -- src/pdes.jl:54-70.
+    The reference hands the RHS closure to ODE.jl's adaptive ode45/ode78 (third-party); this
+    drop-in adds the fixed-step order="4" branch that runs resident on the GPU.  Returns
+    (times, [state_i]) with state = [u; v] like ODE.jl's (tout, yout)."""
+    if order not in ("4",):
+        raise ValueError("ArgumentError(:order): the B200 path implements order=\"4\" (fixed-step RK4)")
+    plan = get_plan(D, k, n, scheme)
+    if dt is None:
+        dt = 0.25 * 2.785 / (math.sqrt(D) * 8.081 * (1 << n))   # RK4 stability, rho(H) = 8.081 2^n
+    times = np.linspace(time0, time1, nout)
+    u, v = _f64(f0coeffs).copy(), _f64(v0coeffs).copy()
+    states = [np.concatenate([u, v])]
+    for t0, t1 in zip(times[:-1], times[1:]):
+        ns, h = _steps(t0, t1, dt)
+        u, v = plan.rk4_wave(u, v, h, ns)
+        states.append(np.concatenate([u, v]))
+    return times, states
+
+
+def advect_evolve(D: int, k: int, n: int, a, u0coeffs, time0: float, time1: float,
+                  scheme: str = "sparse", dt: float | None = None):
+    """u' = -sum_d a_d D_d u from time0 to time1 with fixed-step RK4 (BASELINE config 4; the
+    operator is the one vlasov_evolve applies, src/pdes.jl:179-180)."""
+    plan = get_plan(D, k, n, scheme)
+    if dt is None:
+        dt = 0.5 * 2.785 / (float(np.sum(np.abs(a))) * 8.081 * (1 << n))
+    ns, h = _steps(time0, time1, dt)
+    return plan.rk4_advect(a, u0coeffs, h, ns)
+
+
+def energy_func(D: int, k: int, n: int, soln, scheme: str = "sparse"):
+    """energy_func(D, k, n, soln; scheme) -- src/pdes.jl:258-273."""
+    plan = get_plan(D, k, n, scheme)
+    times, states = soln
+    N = plan.size
+    return np.array(times), np.array([plan.energy(s[:N], s[N:]) for s in states])
+
+
+# ---------------------------------------------------------------------------------------------
+# generic SpMV cross-check
+# ---------------------------------------------------------------------------------------------
+class CsrMatrix:
+    """Resident copy of a reference-style assembled SparseMatrixCSC for the cross-check SpMV."""
+
+    def __init__(self, A, device: int = 0):
+        import scipy.sparse as sp
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        self.shape = A.shape
+        colptr = A.indptr.astype(np.int64) + 1
+        rowval = A.indices.astype(np.int64) + 1
+        nzval = _f64(A.data)
+        h = C.c_void_p()
+        check(lib.gsg_csr_create(A.shape[0], A.shape[1], _ptr(colptr), _ptr(rowval), _ptr(nzval), device, C.byref(h)))
+        self._h = h
+
+    def __matmul__(self, x):
+        x = _f64(x)
+        y = np.empty(self.shape[0])
+        check(lib.gsg_csr_apply(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    __mul__ = __matmul__
+
+    def apply_dev(self, x, y, stream=None) -> None:
+        s = getattr(stream, "cuda_stream", stream)
+        check(lib.gsg_csr_apply_dev(self._h, _devptr(x), _devptr(y), C.c_void_p(int(s) if s else 0)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.gsg_csr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def spmv_csc(A, x) -> np.ndarray:
+    """y = A * x on the GPU for a SparseMatrixCSC-style matrix (`*(RHS, x)`, src/pdes.jl:63)."""
+    import scipy.sparse as sp
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    colptr = A.indptr.astype(np.int64) + 1
+    rowval = A.indices.astype(np.int64) + 1
+    nzval = _f64(A.data)
+    x = _f64(x)
+    y = np.empty(A.shape[0])
+    check(lib.gsg_spmv_csc(A.shape[0], A.shape[1], _ptr(colptr), _ptr(rowval), _ptr(nzval), _ptr(x), _ptr(y)))
+    return y

@@ -1,0 +1,390 @@
+// kernels.cuh -- sm_100a fp64 kernels of libgsgb200: matrix-free tensor-product sweeps
+// y = alpha * D_d x + beta * y over (multi-level, multi-cell, multi-mode) blocks, the RK stage
+// updates, batched reconstruct_DG and the CSR cross-check SpMV.
+//
+// Data model.  For sweep axis d the state decomposes into POLE GROUPS:
+// all multi-level blocks that agree in the other D-1 levels.  A group with other-level sum s has
+// poles of NQ = 2^p one-dimensional cells (p = n - s; N' = K * NQ entries) and every pole is
+// multiplied by the principal sub-block M[0:N', 0:N'] of the 1-D matrix
+// (src/multidim_derivative.jl:30-55).  Inside a group an ITEM r fixes the
+// other dims' cells; for every 1-D cell q the item owns one contiguous multi-cell of KD = K^D
+// doubles at  base[level(q)] + KD * (lo + S * (c(q) + C(level(q)) * hi)),  r = lo + S * hi.
+// Within a multi-cell the entry (a, m_d, b) sits at  a + A*m_d + K*A*b  with A = K^(d-1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsgk {
+
+constexpr int MAXL = 16;
+
+struct GroupDev {
+    long long base[MAXL + 1];  // block offset for level_d = 0..p
+    int p;                     // pole has 2^p cells
+    int S;                     // prod of cells of dims < d
+    int nitems;                // S * prod of cells of dims > d
+    int pad;
+};
+
+struct TileDev {
+    int group;
+    int r0;     // first item
+    int nr;     // number of consecutive items
+    int ebase;  // in-cell offset of the tile's pole sub-range (0 for whole-item tiles)
+};
+
+struct Bcsr {                 // K x K block CSR of the 1-D matrix, block columns ascending
+    const int* rowptr;
+    const int* col;
+    const double* val;        // blocks of KK2 doubles, row-major (m_out, m_in)
+    int KK2;                  // K*K rounded up to even (16-byte aligned blocks)
+};
+
+__device__ __forceinline__ void q_decode(int q, int& ld, int& cd, int& Cd) {
+    ld = q == 0 ? 0 : 32 - __clz(q);
+    cd = q == 0 ? 0 : q - (1 << (ld - 1));
+    Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+}
+
+__device__ __forceinline__ long long cell_addr(const long long* base, int S, int q, int r, int KD) {
+    int ld, cd, Cd;
+    q_decode(q, ld, cd, Cd);
+    const int lo = r % S, hi = r / S;
+    return base[ld] + (long long)KD * (lo + (long long)S * (cd + (long long)Cd * hi));
+}
+
+// ------------------------------------------------------------------------------------------
+// Short poles: N' = K << P <= 32.  One CTA stages whole items (every 1-D cell's KD-double
+// multi-cell, coalesced) in shared memory, one thread owns one pole, holds it in registers,
+// multiplies by the dense N' x N' block broadcast from shared memory, writes back in place.
+// ------------------------------------------------------------------------------------------
+template <int K, int P>
+__global__ void __launch_bounds__(256)
+sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
+                   const GroupDev* __restrict__ groups, const TileDev* __restrict__ tiles,
+                   const double* __restrict__ Mdense, int KD, int A) {
+    constexpr int NQ = 1 << P, NP = K * NQ;
+    extern __shared__ __align__(16) double smem[];
+    double* Hs = smem;                                   // NP*NP (padded to even)
+    double* xs = smem + ((NP * NP + 1) & ~1);            // NQ * nr * KD
+    __shared__ long long sbase[MAXL + 1];
+    __shared__ int sS;
+
+    const TileDev t = tiles[blockIdx.x];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (tid <= P) sbase[tid] = groups[t.group].base[tid];
+    if (tid == 32) sS = groups[t.group].S;
+    for (int i = tid; i < NP * NP; i += nth) Hs[i] = Mdense[i];
+    __syncthreads();
+    const int S = sS;
+    const int nr = t.nr;
+    const int ncell = NQ * nr;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
+
+    // ---- stage in: one warp per multi-cell, lanes stride the KD contiguous doubles
+    for (int c = warp; c < ncell; c += nwarp) {
+        const int q = c / nr, r = c - q * nr;
+        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KD);
+        double* dst = xs + (size_t)c * KD;
+        int e = lane;
+        for (; e + 96 < KD; e += 128) {
+            const double v0 = src[e], v1 = src[e + 32], v2 = src[e + 64], v3 = src[e + 96];
+            dst[e] = v0; dst[e + 32] = v1; dst[e + 64] = v2; dst[e + 96] = v3;
+        }
+        for (; e < KD; e += 32) dst[e] = src[e];
+    }
+    __syncthreads();
+
+    // ---- compute: thread per pole
+    const int PI = KD / K;            // poles per item
+    const int npole = nr * PI;
+    const int KA = K * A;
+    for (int pj = tid; pj < npole; pj += nth) {
+        const int r = pj / PI, j = pj - r * PI;
+        const int b = j / A, a = j - b * A;
+        double* pole = xs + (size_t)r * KD + a + KA * b;     // + q*nr*KD + A*m
+        double x[NP];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int m = 0; m < K; ++m) x[q * K + m] = pole[(size_t)q * nr * KD + A * m];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const int i = q * K + m;
+                double acc = 0.0;
+#pragma unroll
+                for (int jx = 0; jx < NP; ++jx) acc = fma(Hs[i * NP + jx], x[jx], acc);
+                pole[(size_t)q * nr * KD + A * m] = acc;
+            }
+    }
+    __syncthreads();
+
+    // ---- stage out with the epilogue y = alpha*Mx + beta*y
+    for (int c = warp; c < ncell; c += nwarp) {
+        const int q = c / nr, r = c - q * nr;
+        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KD);
+        const double* srcs = xs + (size_t)c * KD;
+        if (beta == 0.0) {
+            for (int e = lane; e < KD; e += 32) dstg[e] = alpha * srcs[e];
+        } else {
+            int e = lane;
+            for (; e + 96 < KD; e += 128) {
+                const double y0 = dstg[e], y1 = dstg[e + 32], y2 = dstg[e + 64], y3 = dstg[e + 96];
+                dstg[e] = fma(alpha, srcs[e], beta * y0);
+                dstg[e + 32] = fma(alpha, srcs[e + 32], beta * y1);
+                dstg[e + 64] = fma(alpha, srcs[e + 64], beta * y2);
+                dstg[e + 96] = fma(alpha, srcs[e + 96], beta * y3);
+            }
+            for (; e < KD; e += 32) dstg[e] = fma(alpha, srcs[e], beta * dstg[e]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic poles (any p, any K): a tile holds PT = nr * NPOLE poles; x is staged TRANSPOSED in
+// shared memory as xs[row = q*K+m][pole] so that lanes = poles read conflict-free; each thread
+// computes one block-row (K outputs) of one pole from the K x K block-CSR matrix (uniform,
+// L1/L2-resident loads), writes ys, and the tile is streamed back coalesced.
+//   TL = K * NPOLE contiguous-or-strided entries per (cell, item):
+//   t -> a = t % Amin, m = (t / Amin) % K, bl = t / (K*Amin);  pole = a + Amin*bl,
+//   in-cell offset e = ebase + a + A*m + K*A*bl.
+// K == 0 instantiates the run-time-k fallback (k up to 10).
+// ------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
+                     const GroupDev* __restrict__ groups, const TileDev* __restrict__ tiles,
+                     Bcsr M, int krt, int p, int KD, int A, int NPOLE, int Amin) {
+    constexpr int KC = K ? K : 10;
+    const int kk = K ? K : krt;
+    const int NQ = 1 << p, NP = kk * NQ;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ long long sbase[MAXL + 1];
+    __shared__ int sS;
+
+    const TileDev t = tiles[blockIdx.x];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nr = t.nr, PT = nr * NPOLE, TL = kk * NPOLE;
+    double* xs = smem;
+    double* ys = smem + (size_t)NP * PT;
+    int* tab_s = reinterpret_cast<int*>(ys + (size_t)NP * PT);   // TL entries: m*PT + pole
+    int* tab_g = tab_s + TL;                                      // TL entries: in-cell offset
+
+    if (tid <= p) sbase[tid] = groups[t.group].base[tid];
+    if (tid == 32) sS = groups[t.group].S;
+    for (int tt = tid; tt < TL; tt += nth) {
+        const int a = tt % Amin, rest = tt / Amin;
+        const int m = rest % kk, bl = rest / kk;
+        tab_s[tt] = m * PT + a + Amin * bl;
+        tab_g[tt] = t.ebase + a + A * m + kk * A * bl;
+    }
+    __syncthreads();
+    const int S = sS;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
+    const int ncell = NQ * nr;
+
+    for (int c = warp; c < ncell; c += nwarp) {
+        const int q = c / nr, r = c - q * nr;
+        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KD);
+        double* dst = xs + (size_t)q * kk * PT + r * NPOLE;
+        for (int tt = lane; tt < TL; tt += 32) dst[tab_s[tt]] = src[tab_g[tt]];
+    }
+    __syncthreads();
+
+    const int nunit = NQ * PT;
+    for (int u = tid; u < nunit; u += nth) {
+        const int q = u / PT, pt = u - q * PT;
+        double acc[KC];
+#pragma unroll
+        for (int m = 0; m < KC; ++m) acc[m] = 0.0;
+        const int b1 = M.rowptr[q + 1];
+        for (int blk = M.rowptr[q]; blk < b1; ++blk) {
+            const int qc = __ldg(M.col + blk);
+            if (qc >= NQ) break;
+            const double* xv = xs + (size_t)qc * kk * PT + pt;
+            const double* hv = M.val + (size_t)blk * M.KK2;
+            double xr[KC];
+#pragma unroll
+            for (int mi = 0; mi < KC; ++mi)
+                if (mi < kk) xr[mi] = xv[mi * PT];
+#pragma unroll
+            for (int mo = 0; mo < KC; ++mo)
+                if (mo < kk) {
+#pragma unroll
+                    for (int mi = 0; mi < KC; ++mi)
+                        if (mi < kk) acc[mo] = fma(__ldg(hv + mo * kk + mi), xr[mi], acc[mo]);
+                }
+        }
+        double* yv = ys + (size_t)q * kk * PT + pt;
+#pragma unroll
+        for (int mo = 0; mo < KC; ++mo)
+            if (mo < kk) yv[mo * PT] = acc[mo];
+    }
+    __syncthreads();
+
+    for (int c = warp; c < ncell; c += nwarp) {
+        const int q = c / nr, r = c - q * nr;
+        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KD);
+        const double* srcs = ys + (size_t)q * kk * PT + r * NPOLE;
+        if (beta == 0.0) {
+            for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * srcs[tab_s[tt]];
+        } else {
+            for (int tt = lane; tt < TL; tt += 32) {
+                const int g = tab_g[tt];
+                dstg[g] = fma(alpha, srcs[tab_s[tt]], beta * dstg[g]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// RK stage updates (classical RK4)
+//   w   = u + cw * k
+//   acc = (first ? u : acc) + ca * k
+// and the final  u = acc + ca * k.
+// ------------------------------------------------------------------------------------------
+__global__ void rk_stage_kernel(long long N, const double* __restrict__ u, const double* __restrict__ k,
+                                double* __restrict__ acc, double* __restrict__ w, double cw, double ca,
+                                int first) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const double ui = u[i], ki = k[i];
+        const double ai = first ? ui : acc[i];
+        w[i] = fma(cw, ki, ui);
+        acc[i] = fma(ca, ki, ai);
+    }
+}
+
+__global__ void rk_final_kernel(long long N, double* __restrict__ u, const double* __restrict__ k,
+                                const double* __restrict__ acc, double ca) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        u[i] = fma(ca, k[i], acc[i]);
+}
+
+__global__ void sumsq_kernel(long long N, const double* __restrict__ x, double* __restrict__ out) {
+    double s = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        s = fma(x[i], x[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) ws[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = lane < (blockDim.x >> 5) ? ws[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(out, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched reconstruct_DG (src/dg_methods.jl:150-165): one warp per point.
+//   1. the warp fills a per-point table of the D*(n+1)*K one-dimensional basis values
+//      v(k, l, cell(x_i,l), m, x_i) and the cell indices (src/dg_methods.jl:27-36,70-79);
+//   2. lanes stride the K^D coefficients of the point's cell in every multi-level block,
+//      multiply by the product of the D table entries (accumulated from 1.0 over i = 1..D as
+//      `V` does, src/dg_methods.jl:47-54) and accumulate; one warp reduction per point.
+// Basis tables: leg[(K_MAX+1) x 2(K_MAX+1)], dg[k x 2k] exactly as the reference stores them.
+// ------------------------------------------------------------------------------------------
+struct ReconTables {
+    const unsigned char* blk_level;   // nblocks * D  (0-based levels)
+    const long long* blk_offset;      // nblocks
+    const double* leg;                // (KMAX+1) * 2(KMAX+1)
+    const double* dg;                 // k * 2k
+    int nblocks, D, k, n, KD, legw;   // legw = 2*(KMAX+1)
+};
+
+__device__ __forceinline__ double poly_eval(const double* __restrict__ v, int half, double x) {
+    // array2poly, src/1d_dg_functions.jl:15-28
+    if (fabs(x) > 1.0) return 0.0;
+    const bool neg = signbit(x);
+    double s = 0.0;
+    for (int i = half - 1; i >= 0; --i) {
+        const double t = neg ? -v[i + half] : v[i + half];
+        s = __dadd_rn(__dmul_rn(s, x), v[i] + t);
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+reconstruct_kernel(ReconTables T, const double* __restrict__ coeffs, const double* __restrict__ pts,
+                   long long npts, double* __restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int D = T.D, k = T.k, n1 = T.n + 1;
+    const int ntab = D * n1 * k;
+    double* bt = smem + (size_t)warp * (ntab + D * n1);           // basis values [d][l][m]
+    int* ci = reinterpret_cast<int*>(bt + ntab);                  // cell index [d][l] (0-based)
+    const double sqrt2 = sqrt(2.0);
+
+    for (long long pt = (long long)blockIdx.x * nwarp + warp; pt < npts; pt += (long long)gridDim.x * nwarp) {
+        __syncwarp();
+        for (int idx = lane; idx < ntab; idx += 32) {
+            const int m = idx % k, dl = idx / k, l = dl % n1, d = dl / n1;
+            const double x = pts[pt * D + d];
+            long long cell;   // 1-based, src/dg_methods.jl:70-79
+            if (l <= 1) cell = 1;
+            else if (x >= 1.0) cell = 1LL << (l - 1);
+            else cell = 1 + (long long)floor((double)(1LL << (l - 1)) * x);
+            double val;
+            if (l == 0) {
+                val = poly_eval(T.leg + m * T.legw, T.legw / 2, 2.0 * x - 1.0) * sqrt2;
+            } else {
+                const double sc = (double)(1LL << l);
+                val = poly_eval(T.dg + m * 2 * k, k, sc * x - (double)(2 * cell - 1)) * sqrt(sc);
+            }
+            bt[idx] = val;
+            if (m == 0) ci[dl] = (int)(cell - 1);
+        }
+        __syncwarp();
+        double acc = 0.0;
+        for (int b = 0; b < T.nblocks; ++b) {
+            const unsigned char* lv = T.blk_level + (size_t)b * D;
+            long long lin = 0, stride = 1;
+            for (int d = 0; d < D; ++d) {
+                const int l = lv[d];
+                lin += (long long)ci[d * n1 + l] * stride;
+                stride *= (l <= 1) ? 1 : (1LL << (l - 1));
+            }
+            const double* cf = coeffs + T.blk_offset[b] + lin * T.KD;
+            for (int e = lane; e < T.KD; e += 32) {
+                int rem = e;
+                double prod = 1.0;
+                for (int d = 0; d < D; ++d) {
+                    const int m = rem % k;
+                    rem /= k;
+                    prod *= bt[(d * n1 + lv[d]) * k + m];
+                }
+                acc = fma(cf[e], prod, acc);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[pt] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR SpMV cross-check: LANES lanes per row, int32 columns.
+// ------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(256)
+spmv_csr_kernel(long long nrows, const long long* __restrict__ rowptr, const int* __restrict__ col,
+                const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = gid / LANES;
+    const int sub = (int)(gid % LANES);
+    double s = 0.0;
+    if (row < nrows) {
+        const long long e = rowptr[row + 1];
+        for (long long p = rowptr[row] + sub; p < e; p += LANES) s = fma(val[p], __ldg(x + col[p]), s);
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (row < nrows && sub == 0) y[row] = s;
+}
+
+}  // namespace gsgk

@@ -1,0 +1,13 @@
+"""Import shim: the package directory is named `galerkinsparsegrids.jl_b200` (with a dot, as the
+build contract requires), which a plain `import` statement cannot spell.  `import gsg_b200`
+loads that directory as the module `gsg_b200`."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "galerkinsparsegrids.jl_b200")
+_spec = _u.spec_from_file_location("gsg_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["gsg_b200"] = _mod
+_spec.loader.exec_module(_mod)

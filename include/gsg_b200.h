@@ -1,0 +1,136 @@
+/* gsg_b200.h -- C ABI of libgsgb200.so: the B200-native drop-in for the hot path of
+ * GalerkinSparseGrids.jl (apply the sparse-grid DG derivative / gradient / Laplacian
+ * operator inside every Runge-Kutta right-hand side, plus batched reconstruct_DG).
+ *
+ * The reference has no FFI of its own (it is pure Julia); the swap points are the Julia
+ * dispatch sites listed per function below (paths relative to the reference root).
+ * INTEGRATION.md shows the `ccall` shim a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative gsg_status on failure;
+ *     gsg_last_error() returns a thread-local, NUL-terminated message.
+ *   - no exceptions cross the boundary; host pointers are never retained past the call.
+ *   - vectors use the reference's vector-hierarchical layout (src/dg_vmethods.jl:48-73).
+ *   - sparse matrices cross as Julia's SparseMatrixCSC{Float64,Int64} fields
+ *     {m, n, colptr[n+1], rowval[nnz], nzval[nnz]} with 1-BASED Int64 indices
+ *     (the five fields the reference itself serialises, src/pdes.jl:149-155).
+ *   - `scheme`: 0 = "sparse", 1 = "full" (src/schemes.jl:21-27).
+ *   - `d` (sweep axis) is 1-BASED as in the reference (src/multidim_derivative.jl:61).
+ *   - *_dev entry points take device pointers and a cudaStream_t (as void*) and are
+ *     asynchronous on that stream; the host-pointer entry points synchronise before
+ *     returning.  There is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with GSG_ERR_CUDA.
+ */
+#ifndef GSG_B200_H
+#define GSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GSG_OK = 0,
+    GSG_ERR_ARG = -1,      /* invalid argument (mirrors Julia's ArgumentError / DomainError) */
+    GSG_ERR_CUDA = -2,     /* CUDA runtime failure or no device                                */
+    GSG_ERR_ALLOC = -3,    /* host or device allocation failure                               */
+    GSG_ERR_UNSUPPORTED = -4
+} gsg_status;
+
+typedef struct gsg_plan gsg_plan;      /* operator plan: index set + device tables + 1-D matrices */
+typedef struct gsg_csr gsg_csr;        /* resident generic sparse matrix (cross-check SpMV)        */
+
+/* ---- diagnostics -------------------------------------------------------------------- */
+int gsg_version(void);
+const char* gsg_last_error(void);
+/* writes "name;sm_count;cc_major.cc_minor;global_mem_bytes" */
+int gsg_device_info(int device, char* buf, size_t buflen);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t gsg_launch_count(void);
+
+/* ---- host-side setup mirrors (CPU only; these are what the Julia host computes itself) -- */
+/* get_size(Val(D), k, n, Val(scheme))                        src/dg_vmethods.jl:35-45 */
+int gsg_get_size(int D, int k, int n, int scheme, int64_t* size_out);
+/* v(k, level, cell, mode, x) for an array of x; level 0-based, cell/mode 1-based
+ *                                                             src/dg_methods.jl:27-36 */
+int gsg_basis_v(int k, int level, int cell, int mode, const double* x, int64_t npts, double* out);
+/* cell_index(x, l)                                            src/dg_methods.jl:70-79 */
+int gsg_cell_index(double x, int level, int64_t* cell_out);
+/* leg_coeffs (K_max+1 rows of 2(K_max+1)) and dg_coeffs[k] (k rows of 2k)
+ *                                                             src/1d_dg_functions.jl:35,52-62 */
+int gsg_basis_tables(int k, double* leg_out, double* dg_out);
+/* periodic_DLF_matrix(k, n; basis="hier"|"pos")               src/1d_derivative.jl:136-148
+ * two-call pattern: pass nzval == NULL to query nnz.  basis: 0 = hier, 1 = pos. */
+int gsg_dlf_matrix(int k, int n, int basis, int64_t* nnz_inout,
+                   int64_t* colptr, int64_t* rowval, double* nzval);
+/* tensor_construct(D, k, n, [v_1..v_D]; scheme) on 1-D coefficient vectors of length k*2^n,
+ * result in vector layout                                     src/tensor_construct.jl:19-63 */
+int gsg_tensor_construct(int D, int k, int n, int scheme, const double* const* vcoeffs_1d,
+                         double* out);
+
+/* ---- plan ----------------------------------------------------------------------------- */
+/* Replaces the construction of grad_matrix / laplacian_matrix (src/pdes.jl:59,141;
+ * src/multidim_derivative.jl:19-79).  H = periodic_DLF_matrix(k, n) is handed over verbatim
+ * (SURVEY.md headline fact 4: values as stored, noise entries included). */
+int gsg_plan_create(int D, int k, int n, int scheme,
+                    int64_t H_n, const int64_t* H_colptr, const int64_t* H_rowval,
+                    const double* H_nzval, int device, gsg_plan** plan_out);
+int gsg_plan_destroy(gsg_plan* plan);
+int gsg_plan_size(const gsg_plan* plan, int64_t* size_out);
+/* run all subsequent work of this plan on `stream` (cudaStream_t); NULL = the plan's own */
+int gsg_plan_set_stream(gsg_plan* plan, void* stream);
+int gsg_plan_sync(gsg_plan* plan);
+
+/* ---- operator apply, host vectors (drop-in for `A*x`) ------------------------------------ */
+/* y = D_d * x             `Ds[d] * f_modal`  src/pdes.jl:179-180, `D_ops[j]*u` :268 */
+int gsg_apply_D(gsg_plan* plan, int d, const double* x, double* y);
+/* y = sum_d a[d] * D_d x  (gradient combination; a has D entries) */
+int gsg_apply_grad(gsg_plan* plan, const double* a, const double* x, double* y);
+/* y = sum_d D_d (D_d x)   `laplacian_matrix(D,k,n) * x`  src/multidim_derivative.jl:71-79 */
+int gsg_apply_laplacian(gsg_plan* plan, const double* x, double* y);
+
+/* ---- operator apply, device vectors --------------------------------------------------------- */
+/* y = alpha * D_d x + beta * y   (beta == 0: y is not read) */
+int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, double beta,
+                    double* y_dev);
+/* y = sum_d a[d] D_d x */
+int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, double* y_dev);
+int gsg_apply_laplacian_dev(gsg_plan* plan, const double* x_dev, double* y_dev, double* tmp_dev);
+
+/* ---- fused fixed-step RK4 evolutions, state resident on device ------------------------- */
+/* u' = -sum_d a[d] D_d u  (the operator vlasov_evolve applies, src/pdes.jl:179-180;
+ * BASELINE config 4).  Classical RK4, stage order in DESIGN.md.  y is updated in place. */
+int gsg_rk4_advect(gsg_plan* plan, const double* a, double* y, double dt, int64_t nsteps);
+int gsg_rk4_advect_dev(gsg_plan* plan, const double* a, double* y_dev, double dt, int64_t nsteps);
+/* [u; v]' = [v; L u]   (`wave_data`, src/pdes.jl:22-49; RHS closure :63) */
+int gsg_rk4_wave(gsg_plan* plan, double* u, double* v, double dt, int64_t nsteps);
+int gsg_rk4_wave_dev(gsg_plan* plan, double* u_dev, double* v_dev, double dt, int64_t nsteps);
+/* E = sum_d |D_d u|^2 + |udot|^2     energy_func, src/pdes.jl:258-273 */
+int gsg_energy(gsg_plan* plan, const double* u, const double* udot, double* energy_out);
+
+/* ---- batched reconstruct_DG -------------------------------------------------------------------- */
+/* out[i] = reconstruct_DG(V2D(vcoeffs), points[:, i])   src/dg_methods.jl:150-165;
+ * points is a column-major D x npts matrix (Julia Matrix{Float64}).  Called once per point
+ * by mcerr's loop in the reference (src/error_measure.jl:12-19,39-41). */
+int gsg_reconstruct(gsg_plan* plan, const double* vcoeffs, const double* points, int64_t npts,
+                    double* out);
+int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double* points_dev,
+                        int64_t npts, double* out_dev);
+
+/* ---- generic SpMV on the reference's assembled matrix (correctness / perf cross-check) ------ */
+/* y = A * x with A a Julia SparseMatrixCSC (1-based Int64)   `*(RHS, x)` src/pdes.jl:63 */
+int gsg_spmv_csc(int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                 const double* nzval, const double* x, double* y);
+/* resident variant: upload once (converted to CSR int32 on the way), apply many times */
+int gsg_csr_create(int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                   const double* nzval, int device, gsg_csr** out);
+int gsg_csr_destroy(gsg_csr* A);
+int gsg_csr_apply(gsg_csr* A, const double* x, double* y);
+int gsg_csr_apply_dev(gsg_csr* A, const double* x_dev, double* y_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSG_B200_H */

@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libgsgb200.so) against the CPU oracle
+on the same seeded inputs.  Tolerance: 1e-12 relative in Float64 (BASELINE.json north_star),
+measured as ||y_gpu - y_oracle||_2 / ||y_oracle||_2."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import f_cos, f_gauss, f_sin, product_state, random_state, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+# (D, k, n, scheme): small enough for the oracle to finish in seconds; covers every kernel
+# class (register-resident short poles, generic block-CSR long poles, run-time-k fallback),
+# both schemes, k = 1..6 and D = 1..6.
+CASES = [
+    (1, 3, 5, "sparse"),      # BASELINE config 1 size
+    (2, 3, 6, "sparse"),
+    (2, 3, 4, "full"),
+    (3, 3, 5, "sparse"),
+    (4, 3, 4, "sparse"),
+    (6, 3, 3, "sparse"),
+    (2, 1, 5, "sparse"),
+    (2, 2, 6, "sparse"),
+    (3, 2, 4, "full"),
+    (2, 4, 5, "sparse"),
+    (3, 4, 3, "sparse"),
+    (2, 5, 4, "sparse"),
+    (2, 6, 3, "sparse"),      # run-time-k fallback kernel
+    (5, 2, 3, "sparse"),
+]
+
+
+@pytest.fixture(scope="module")
+def plans(gsg, oracle):
+    cache = {}
+
+    def get(D, k, n, scheme):
+        key = (D, k, n, scheme)
+        if key not in cache:
+            H = oracle.periodic_DLF_matrix(k, n)
+            import scipy.sparse as sp
+            Hs = sp.csc_matrix((H.nzval, H.rowval, H.colptr), shape=(H.m, H.n))
+            # the SAME 1-D matrix is handed to the GPU plan and to the oracle
+            cache[key] = (gsg.Plan(D, k, n, scheme, H=Hs), H)
+        return cache[key]
+
+    return get
+
+
+@pytest.mark.parametrize("D,k,n,scheme", CASES)
+def test_apply_D_every_axis(plans, oracle, D, k, n, scheme):
+    plan, H = plans(D, k, n, scheme)
+    N = oracle.get_size(D, k, n, scheme)
+    assert plan.size == N
+    x = random_state(N, seed=D * 100 + k * 10 + n)
+    for d in range(1, D + 1):
+        y_ref = oracle.apply_D_poles(D, d, k, n, x, scheme=scheme, H=H)
+        y = plan.apply_D(d, x)
+        assert relerr(y, y_ref) <= TOL, (d, relerr(y, y_ref))
+
+
+@pytest.mark.parametrize("D,k,n", [(2, 3, 6), (3, 3, 5), (4, 3, 4)])
+@pytest.mark.parametrize("f", [f_sin, f_gauss])
+def test_apply_D_synthetic_initial_conditions(plans, oracle, D, k, n, f):
+    """sin-product and Gaussian data, as north_star names them."""
+    plan, H = plans(D, k, n, "sparse")
+    x = product_state(oracle, D, k, n, f)
+    for d in (1, D):
+        y_ref = oracle.apply_D_poles(D, d, k, n, x, H=H)
+        assert relerr(plan.apply_D(d, x), y_ref) <= TOL
+
+
+def test_apply_D_matches_literal_assembly(plans, oracle):
+    """Cross-check against the literal Dict-loop assembly of
+    src/multidim_derivative.jl:19-58 applied by CSC column scatter (src/pdes.jl:63)."""
+    D, k, n = 2, 3, 4
+    plan, H = plans(D, k, n, "sparse")
+    x = random_state(plan.size, seed=7)
+    for d in (1, 2):
+        A = oracle.D_matrix_literal(D, d, k, n, H=H)
+        assert relerr(plan.apply_D(d, x), A.matvec(x)) <= TOL
+
+
+@pytest.mark.parametrize("D,k,n,scheme", [(2, 3, 6, "sparse"), (4, 3, 4, "sparse"), (3, 2, 4, "full")])
+def test_apply_grad_and_laplacian(plans, oracle, D, k, n, scheme):
+    plan, H = plans(D, k, n, scheme)
+    x = random_state(plan.size, seed=11)
+    a = np.linspace(0.5, 1.5, D)
+    mats = [oracle.D_matrix_poles(D, d, k, n, scheme=scheme, H=H) for d in range(1, D + 1)]
+    g_ref = sum(ad * (A @ x) for ad, A in zip(a, mats))
+    assert relerr(plan.apply_grad(a, x), g_ref) <= TOL
+    l_ref = sum(A @ (A @ x) for A in mats)
+    # (D*D)x vs D(Dx): rounding floor ~8e-13 relative at n=8; small n here
+    assert relerr(plan.apply_laplacian(x), l_ref) <= TOL
+
+
+@pytest.mark.parametrize("D,k,n", [(2, 3, 5), (4, 3, 4)])
+@pytest.mark.parametrize("f", [f_sin, f_gauss])
+def test_rk4_advect_fixed_steps(plans, oracle, D, k, n, f):
+    """RK4 state after a FIXED number of steps at fixed dt."""
+    plan, H = plans(D, k, n, "sparse")
+    u0 = product_state(oracle, D, k, n, f)
+    a = np.ones(D)
+    mats = [oracle.D_matrix_poles(D, d, k, n, H=H) for d in range(1, D + 1)]
+    dt, nsteps = 1.0e-4, 16
+    ref = oracle.rk4(oracle.advect_rhs(mats, a), u0, dt, nsteps)
+    out = plan.rk4_advect(a, u0, dt, nsteps)
+    assert relerr(out, ref) <= TOL
+    assert relerr(out, u0) > 1e-6          # the state actually moved
+
+
+def test_rk4_wave_fixed_steps(plans, oracle):
+    D, k, n = 2, 3, 5
+    plan, H = plans(D, k, n, "sparse")
+    u0 = product_state(oracle, D, k, n, f_sin)
+    v0 = np.zeros_like(u0)
+    mats = [oracle.D_matrix_poles(D, d, k, n, H=H) for d in range(1, D + 1)]
+    dt, nsteps = 2.0e-4, 16
+    ref = oracle.rk4(oracle.wave_rhs(mats), np.concatenate([u0, v0]), dt, nsteps)
+    u, v = plan.rk4_wave(u0, v0, dt, nsteps)
+    assert relerr(np.concatenate([u, v]), ref) <= TOL
+    e0 = oracle.energy(mats, np.concatenate([u0, v0]))
+    assert abs(plan.energy(u0, v0) - e0) <= 1e-12 * e0
+    # test/solvers.jl:64-75: sqrt(E) ~ sqrt(2) pi for sin(2 pi x) sin(2 pi y)
+    assert abs(math.sqrt(plan.energy(u, v)) - math.sqrt(2) * math.pi) < 1e-4
+
+
+@pytest.mark.parametrize("D,k,n,scheme", [(1, 3, 5, "sparse"), (2, 3, 4, "sparse"), (2, 2, 3, "full"),
+                                          (3, 4, 3, "sparse"), (4, 3, 3, "sparse")])
+def test_reconstruct(plans, oracle, D, k, n, scheme):
+    plan, _ = plans(D, k, n, scheme)
+    vect = product_state(oracle, D, k, n, f_sin, scheme=scheme) + 0.1 * product_state(oracle, D, k, n, f_gauss, scheme=scheme)
+    rng = np.random.default_rng(20240)
+    pts = rng.random((64, D))
+    pts[0, :] = 0.0          # edges of the domain and cell boundaries
+    pts[1, :] = 1.0
+    pts[2, :] = 0.5
+    pts[3, :] = 0.25
+    ref = np.array([oracle.reconstruct_DG(D, k, n, vect, list(p), scheme=scheme) for p in pts])
+    out = plan.reconstruct(vect, pts)
+    scale = max(np.abs(ref).max(), 1e-300)
+    assert np.abs(out - ref).max() / scale <= TOL
+
+
+def test_reconstruct_empty_and_single(plans, oracle):
+    plan, _ = plans(2, 3, 4, "sparse")
+    vect = product_state(oracle, 2, 3, 4, f_cos)
+    assert plan.reconstruct(vect, np.empty((0, 2))).shape == (0,)
+    one = plan.reconstruct(vect, np.array([[0.3, 0.7]]))
+    assert abs(one[0] - oracle.reconstruct_DG(2, 3, 4, vect, [0.3, 0.7])) <= 1e-12
+
+
+def test_spmv_cross_check(gsg, plans, oracle):
+    """CSR SpMV on the reference-style assembled matrix agrees with the matrix-free sweep."""
+    D, k, n = 3, 3, 4
+    plan, H = plans(D, k, n, "sparse")
+    x = random_state(plan.size, seed=5)
+    for d in (1, 2, 3):
+        A = oracle.D_matrix_poles(D, d, k, n, H=H)
+        y_spmv = gsg.spmv_csc(A, x)
+        assert relerr(y_spmv, A @ x) <= TOL
+        assert relerr(y_spmv, plan.apply_D(d, x)) <= TOL
+    R = gsg.CsrMatrix(A)
+    assert relerr(R @ x, A @ x) <= TOL
+
+
+def test_linearity_and_skew_symmetry_mid_size(plans, oracle):
+    """Size-independent properties at a size the oracle does not assemble: linearity and
+    <x, D y> = -<D x, y> up to the reference's own ||H + H'|| ~ 1e-9 * max|H| noise."""
+    D, k, n = 4, 3, 6
+    plan, H = plans(D, k, n, "sparse")
+    x = random_state(plan.size, seed=1)
+    y = random_state(plan.size, seed=2)
+    for d in (1, 4):
+        Dx, Dy = plan.apply_D(d, x), plan.apply_D(d, y)
+        Dxy = plan.apply_D(d, 2.0 * x - 3.0 * y)
+        assert relerr(Dxy, 2.0 * Dx - 3.0 * Dy) <= 1e-13
+        skew = abs(np.dot(x, Dy) + np.dot(Dx, y)) / (np.linalg.norm(x) * np.linalg.norm(Dy))
+        assert skew < 1e-9
+
+
+def test_error_behaviour(gsg, plans):
+    plan, _ = plans(2, 3, 4, "sparse")
+    with pytest.raises(ValueError):
+        plan.apply_D(1, np.zeros(3))
+    with pytest.raises(gsg.GsgError):
+        plan.apply_D(3, np.zeros(plan.size))
+    with pytest.raises(gsg.GsgError):
+        gsg.Plan(2, 11, 3)          # DomainError: k > K_max (src/1d_dg_functions.jl:39)
+    with pytest.raises(ValueError):
+        gsg.get_size(2, 3, 3, scheme="energy")

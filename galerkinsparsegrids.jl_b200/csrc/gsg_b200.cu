@@ -47,6 +47,18 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            if (p) cudaFree(p);
+            p = o.p; n = o.n;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
     ~DevBuf() { if (p) cudaFree(p); }
     int upload(const std::vector<T>& h) {
         if (p) { cudaFree(p); p = nullptr; }
@@ -278,6 +290,18 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     return 0;
 }
 
+int launch_check(const char* what, int K, const SweepClass& c) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && getenv("GSG_DEBUG_SYNC")) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s<K=%d> p=%d ntiles=%d smem=%zu NPOLE=%d Amin=%d: %s", what, K, c.p, c.ntiles,
+                 c.smem, c.NPOLE, c.Amin, cudaGetErrorString(e));
+        return fail(GSG_ERR_CUDA, buf);
+    }
+    return 0;
+}
+
 template <int K, int P>
 int launch_short_kp(gsg_plan& pl, const Direction& dir, const SweepClass& c, const double* x, double* y,
                     double alpha, double beta) {
@@ -290,8 +314,7 @@ int launch_short_kp(gsg_plan& pl, const Direction& dir, const SweepClass& c, con
     kern<<<c.ntiles, 256, c.smem, pl.stream>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, pl.dense[P]->p,
                                                 (int)pl.S.kD, dir.A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    GSG_CUDA(cudaGetLastError());
-    return 0;
+    return launch_check("sweep_short", K, c);
 }
 
 template <int K>
@@ -319,8 +342,7 @@ int launch_generic_k(gsg_plan& pl, const Direction& dir, const SweepClass& c, co
     kern<<<c.ntiles, 256, c.smem, pl.stream>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, M, pl.S.k, c.p,
                                                 (int)pl.S.kD, dir.A, c.NPOLE, c.Amin);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    GSG_CUDA(cudaGetLastError());
-    return 0;
+    return launch_check("sweep_generic", K, c);
 }
 
 // y = alpha * D_d x + beta * y   (d 0-based); x and y must not alias

@@ -33,7 +33,8 @@ print(f"tensor_construct {time.time()-t0:.2f}s", flush=True)
 dev = torch.device("cuda:0")
 x = torch.from_numpy(u0).to(dev)
 y = torch.zeros_like(x)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 plan.set_stream(stream)
 
 

@@ -242,6 +242,8 @@ class Plan:
         size = C.c_int64()
         check(lib.gsg_plan_size(self._h, C.byref(size)))
         self.size = size.value
+        check(lib.gsg_plan_dev_size(self._h, C.byref(size)))
+        self.dev_size = size.value      # padded length of device-layout vectors
 
     def close(self):
         if getattr(self, "_h", None):
@@ -315,6 +317,29 @@ class Plan:
 
     def sync(self) -> None:
         check(lib.gsg_plan_sync(self._h))
+
+    def pack_dev(self, ref_vec, dev_vec) -> None:
+        """reference-layout device vector (length size) -> device layout (length dev_size)."""
+        check(lib.gsg_pack_dev(self._h, _devptr(ref_vec), _devptr(dev_vec)))
+
+    def unpack_dev(self, dev_vec, ref_vec) -> None:
+        check(lib.gsg_unpack_dev(self._h, _devptr(dev_vec), _devptr(ref_vec)))
+
+    def to_device(self, host_vec, device="cuda:0"):
+        """numpy reference-layout vector -> zero-padded torch tensor in device layout."""
+        import torch
+        ref = torch.from_numpy(self._vec(host_vec)).to(device)
+        dev = torch.zeros(self.dev_size, dtype=torch.float64, device=device)
+        self.pack_dev(ref, dev)
+        self.sync()
+        return dev
+
+    def to_host(self, dev_vec) -> np.ndarray:
+        import torch
+        ref = torch.empty(self.size, dtype=torch.float64, device=dev_vec.device)
+        self.unpack_dev(dev_vec, ref)
+        self.sync()
+        return ref.cpu().numpy()
 
     def apply_D_dev(self, d: int, x, y, alpha: float = 1.0, beta: float = 0.0) -> None:
         check(lib.gsg_apply_D_dev(self._h, d, alpha, _devptr(x), beta, _devptr(y)))

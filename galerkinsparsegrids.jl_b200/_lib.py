@@ -50,6 +50,9 @@ SIGNATURES = {
     "gsg_plan_create": (i32, [i32, i32, i32, i32, i64, vp, vp, vp, i32, C.POINTER(vp)]),
     "gsg_plan_destroy": (i32, [vp]),
     "gsg_plan_size": (i32, [vp, p_i64]),
+    "gsg_plan_dev_size": (i32, [vp, p_i64]),
+    "gsg_pack_dev": (i32, [vp, vp, vp]),
+    "gsg_unpack_dev": (i32, [vp, vp, vp]),
     "gsg_plan_set_stream": (i32, [vp, vp]),
     "gsg_plan_sync": (i32, [vp]),
     "gsg_apply_D": (i32, [vp, i32, vp, vp]),

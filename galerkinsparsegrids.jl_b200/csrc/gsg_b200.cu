@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -44,7 +45,7 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 template <class T>
-struct DevBuf {
+struct DevBuf {                       // move-only owner of a device allocation
     T* p = nullptr;
     size_t n = 0;
     DevBuf() = default;
@@ -68,11 +69,13 @@ struct DevBuf {
         GSG_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
         return 0;
     }
+    // grow-only; new allocations are zero-filled (the padding slots of state vectors stay finite)
     int resize(size_t m) {
         if (m <= n && p) return 0;
         if (p) { cudaFree(p); p = nullptr; }
         n = m;
         GSG_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        GSG_CUDA(cudaMemset(p, 0, n * sizeof(T)));
         return 0;
     }
 };
@@ -80,14 +83,22 @@ struct DevBuf {
 constexpr int SHORT_MAX_NP = 32;      // register-resident poles up to this length
 constexpr int SHORT_MAX_P = 3;
 constexpr size_t GENERIC_SMEM_BUDGET = 96 * 1024;
+constexpr size_t SMEM_OPTIN_MAX = 227 * 1024;
 constexpr int SHORT_TILE_DOUBLES = 4096;
+constexpr int TMA_STAGE_TARGET_DOUBLES = 5840;
 
-struct SweepClass {          // all tiles of one direction with the same pole length
-    int p = 0;
-    bool is_short = false;
+enum class Kind { SHORT_TMA, SHORT, LONG, GENERIC };
+
+struct SweepClass {          // one launch of a sweep
+    int p = 0;               // pole length class (SHORT_TMA: the largest short class it holds)
+    Kind kind = Kind::GENERIC;
     int NPOLE = 0, Amin = 0; // generic kernel parameters
+    int nwarps = 8;          // long kernel: warps per CTA
     size_t smem = 0;
     DevBuf<TileDev> tiles;
+    DevBuf<TileLong> ltiles;
+    DevBuf<TileS> stiles;
+    ShortParams sprm{};
     int ntiles = 0;
 };
 
@@ -110,18 +121,31 @@ struct gsg_plan {
     DevBuf<int> b_rowptr, b_col;
     DevBuf<double> b_val;
     int KK2 = 0;
-    std::vector<std::unique_ptr<DevBuf<double>>> dense;   // index p
+    std::vector<std::unique_ptr<DevBuf<double>>> dense;   // index p (legacy short kernel)
+    DevBuf<double> dense_all;                              // concatenated (device copy)
+    std::vector<double> dense_host;                        // concatenated, passed as kernel parameter
+    int hoff[5] = {0, 0, 0, 0, 0};
+    int htotal = 0, short_pmax = -1;
+    std::vector<std::unique_ptr<DevBuf<int>>> ptab;        // index p: [wsplit (nw+1) | rowend (2^p)]
+    std::vector<int> ptab_nw;
 
     std::vector<Direction> dirs;
+
+    // fork/join streams so the launches of one sweep run concurrently
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> ev_done;
+    cudaEvent_t ev_fork = nullptr;
 
     // reconstruct tables
     DevBuf<unsigned char> r_level;
     DevBuf<long long> r_offset;
     DevBuf<double> r_leg, r_dg;
 
-    // workspaces
+    // workspaces (device layout)
     DevBuf<double> wx, wy, wk, wacc, ww, wtmp, wred;
     DevBuf<double> wpts, wout;
+    long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
+    DevBuf<long long> dbgbuf;
 };
 
 struct gsg_csr {
@@ -139,6 +163,10 @@ int pow_int(int b, int e) {
     int r = 1;
     while (e-- > 0) r *= b;
     return r;
+}
+
+bool short_supported(int K, int p) {
+    return K >= 1 && K <= 5 && p <= SHORT_MAX_P && (K << p) <= SHORT_MAX_NP;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -181,21 +209,55 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_rowptr.upload(rowptr));
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
-    P.dense.resize(n + 1);
+
+    // long kernel tables per p: block-rows split over the CTA's warps (balanced in block count)
+    // and the end of each row's blocks inside the principal sub-block
+    P.ptab.resize(n + 1);
+    P.ptab_nw.assign(n + 1, 0);
     for (int p = 0; p <= n; ++p) {
+        const int nq = 1 << p;
+        const int nw = std::min(16, std::max(std::min(4, nq), nq / 4));
+        std::vector<long long> pre(nq + 1, 0);
+        std::vector<int> tab(nw + 1 + nq, 0);
+        for (int q = 0; q < nq; ++q) {
+            int b = rowptr[q];
+            while (b < rowptr[q + 1] && col[b] < nq) ++b;
+            tab[nw + 1 + q] = b;
+            pre[q + 1] = pre[q] + (b - rowptr[q]) + 1;     // +1: per-row epilogue cost
+        }
+        tab[0] = 0;
+        int q = 0;
+        for (int w = 1; w < nw; ++w) {
+            const long long target = pre[nq] * w / nw;
+            while (q < nq && pre[q] < target) ++q;
+            tab[w] = std::max(q, tab[w - 1]);
+        }
+        tab[nw] = nq;
+        P.ptab[p].reset(new DevBuf<int>());
+        GSG_TRY(P.ptab[p]->upload(tab));
+        P.ptab_nw[p] = nw;
+    }
+
+    // dense principal sub-blocks for the register-resident short classes
+    P.dense.resize(n + 1);
+    std::vector<double> all;
+    for (int p = 0; p <= n && p <= SHORT_MAX_P; ++p) {
         const int NP = K << p;
-        if (NP > SHORT_MAX_NP || p > SHORT_MAX_P) break;
+        if (NP > SHORT_MAX_NP) break;
         std::vector<double> d((size_t)NP * NP);
         for (int i = 0; i < NP; ++i)
             for (int j = 0; j < NP; ++j) d[(size_t)i * NP + j] = Hd[(size_t)i * N1 + j];
         P.dense[p].reset(new DevBuf<double>());
         GSG_TRY(P.dense[p]->upload(d));
+        P.hoff[p] = (int)all.size();
+        all.insert(all.end(), d.begin(), d.end());
+        if (all.size() & 1) all.push_back(0.0);
+        P.short_pmax = p;
     }
+    P.htotal = (int)all.size();
+    P.dense_host = all;
+    GSG_TRY(P.dense_all.upload(all));
     return 0;
-}
-
-bool short_supported(int K, int p) {
-    return K >= 1 && K <= 5 && p <= SHORT_MAX_P && (K << p) <= SHORT_MAX_NP;
 }
 
 int build_direction(gsg_plan& P, int d /*0-based*/) {
@@ -203,12 +265,12 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     const int D = S.D, K = S.k, n = S.n;
     Direction& dir = P.dirs[d];
     dir.A = pow_int(K, d);
-    const int KD = (int)S.kD;
+    const int KD = (int)S.kD, KDp = (int)S.kDp;
     const int PI = KD / K;
+    const bool legacy_short = getenv("GSG_SHORT_LEGACY") != nullptr;
 
     // groups keyed by the other dims' levels, in layout order of their level_d = 0 block
     std::vector<GroupDev> groups;
-    std::vector<std::vector<TileDev>> tiles(n + 1);
     for (const gsg::Block& b0 : S.blocks) {
         if (b0.level[d] != 0) continue;
         GroupDev g;
@@ -221,7 +283,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             lv[d] = ld;
             auto it = S.by_level.find(lv);
             if (it == S.by_level.end()) return fail(GSG_ERR_ARG, "internal: missing block");
-            g.base[ld] = S.blocks[it->second].offset;
+            g.base[ld] = S.blocks[it->second].poffset;
         }
         long long Slo = 1, Shi = 1;
         for (int i = 0; i < d; ++i) Slo *= b0.cells[i];
@@ -233,13 +295,97 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     }
     GSG_TRY(dir.groups.upload(groups));
 
+    // ---- merged TMA class for all register-resident pole lengths
+    const bool use_tma = !legacy_short && P.short_pmax >= 0 && K <= 5;
+    if (use_tma) {
+        SweepClass c;
+        c.kind = Kind::SHORT_TMA;
+        c.p = P.short_pmax;
+        const int cmin = 1 << P.short_pmax;
+        int CT = std::max(cmin, (TMA_STAGE_TARGET_DOUBLES / KDp) / cmin * cmin);   // multi-cells per tile
+        const size_t fixed = 128 + (size_t)PI * 4 + 128;
+        int ns = 4;
+        while (ns > 2 && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) --ns;
+        while (CT > cmin && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) CT -= cmin;
+        if (fixed + (size_t)ns * CT * KDp * 8 <= SMEM_OPTIN_MAX) {
+            std::vector<TileS> tl;
+            for (int p = P.short_pmax; p >= 0; --p) {          // largest pole length first
+                const int nr_max = CT >> p;
+                for (size_t gi = 0; gi < groups.size(); ++gi) {
+                    if (groups[gi].p != p) continue;
+                    for (int r0 = 0; r0 < groups[gi].nitems; r0 += nr_max) {
+                        TileS t;
+                        std::memset(&t, 0, sizeof(t));
+                        for (int l = 0; l <= p && l < 4; ++l) t.base[l] = groups[gi].base[l];
+                        t.S = groups[gi].S;
+                        t.r0 = r0;
+                        t.nr = (short)std::min(nr_max, groups[gi].nitems - r0);
+                        t.P = (short)p;
+                        tl.push_back(t);
+                    }
+                }
+            }
+            c.ntiles = (int)tl.size();
+            if (c.ntiles > 0) {
+                GSG_TRY(c.stiles.upload(tl));
+                c.sprm.KD = KD;
+                c.sprm.KDp = KDp;
+                c.sprm.A = dir.A;
+                c.sprm.stage_doubles = CT * KDp;
+                c.sprm.nstage = ns;
+                c.smem = fixed + (size_t)ns * CT * KDp * 8;
+                dir.classes.push_back(std::move(c));
+            }
+        }
+    }
+    const bool tma_active = !dir.classes.empty();
+
     for (int p = 0; p <= n; ++p) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
-        c.is_short = short_supported(K, p);
+        const size_t long_smem = (size_t)NP * 32 * sizeof(double) + (size_t)P.ptab_nw[p] * K * 32 * sizeof(double);
+        if (short_supported(K, p)) {
+            if (tma_active) continue;
+            c.kind = Kind::SHORT;
+        } else if (K <= 5 && long_smem + 2048 <= SMEM_OPTIN_MAX) {
+            c.kind = Kind::LONG;
+        } else {
+            c.kind = Kind::GENERIC;
+        }
+        if (c.kind == Kind::LONG) {
+            std::vector<TileLong> ll;
+            c.nwarps = P.ptab_nw[p];
+            c.smem = long_smem;
+            const int A = dir.A, B = PI / A;
+            for (size_t gi = 0; gi < groups.size(); ++gi) {
+                if (groups[gi].p != p) continue;
+                if (PI >= 32) {
+                    for (int r = 0; r < groups[gi].nitems; ++r) {
+                        if (A >= 32) {
+                            for (int b = 0; b < B; ++b)
+                                for (int a0 = 0; a0 < A; a0 += 32)
+                                    ll.push_back(TileLong{(int)gi, r, a0 + K * A * b, 1, (short)std::min(32, A - a0), 1, 0});
+                        } else {
+                            const int nbmax = 32 / A;
+                            for (int b0 = 0; b0 < B; b0 += nbmax)
+                                ll.push_back(TileLong{(int)gi, r, K * A * b0, 1, (short)A, (short)std::min(nbmax, B - b0), 0});
+                        }
+                    }
+                } else {
+                    const int nrmax = 32 / PI;
+                    for (int r0 = 0; r0 < groups[gi].nitems; r0 += nrmax)
+                        ll.push_back(TileLong{(int)gi, r0, 0, (short)std::min(nrmax, groups[gi].nitems - r0), (short)A, (short)B, 0});
+                }
+            }
+            c.ntiles = (int)ll.size();
+            if (c.ntiles == 0) continue;
+            GSG_TRY(c.ltiles.upload(ll));
+            dir.classes.push_back(std::move(c));
+            continue;
+        }
         std::vector<TileDev> tl;
-        if (c.is_short) {
+        if (c.kind == Kind::SHORT) {
             int nr_max = std::max(1, SHORT_TILE_DOUBLES / (NQ * KD));
             c.NPOLE = PI;
             for (size_t gi = 0; gi < groups.size(); ++gi) {
@@ -285,8 +431,13 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         GSG_TRY(c.tiles.upload(tl));
         dir.classes.push_back(std::move(c));
     }
-    // heavy classes first so their long CTAs overlap the streaming ones
-    std::sort(dir.classes.begin(), dir.classes.end(), [](const SweepClass& a, const SweepClass& b) { return a.p > b.p; });
+    // launch order: the persistent streaming kernel goes on the main stream (index 0); the long
+    // classes follow, longest poles first, each on its own forked stream
+    std::stable_sort(dir.classes.begin(), dir.classes.end(), [](const SweepClass& a, const SweepClass& b) {
+        const int ka = a.kind == Kind::SHORT_TMA ? 1 : 0, kb = b.kind == Kind::SHORT_TMA ? 1 : 0;
+        if (ka != kb) return ka > kb;
+        return a.p > b.p;
+    });
     return 0;
 }
 
@@ -302,82 +453,150 @@ int launch_check(const char* what, int K, const SweepClass& c) {
     return 0;
 }
 
+template <class Kern>
+int ensure_smem(Kern kern, size_t smem, size_t& configured) {
+    if (smem > 48 * 1024 && smem > configured) {
+        GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    return 0;
+}
+
+template <int K>
+int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                     double* y, double alpha, double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        auto kern = sweep_short_tma_kernel<K>;
+        static thread_local size_t configured = 0;
+        GSG_TRY(ensure_smem(kern, c.smem, configured));
+        const int grid = std::min(c.ntiles, pl.sm_count);
+        static_assert(sizeof(HDense<K>) + 256 < 32000, "dense blocks must fit the kernel parameter space");
+        HDense<K> hd;
+        if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
+            return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
+        std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
+        kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
+                                                                         c.stiles.p, c.ntiles, hd, c.sprm, pl.dbg);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return launch_check("sweep_short_tma", K, c);
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: TMA short kernel not instantiated");
+}
+
 template <int K, int P>
-int launch_short_kp(gsg_plan& pl, const Direction& dir, const SweepClass& c, const double* x, double* y,
-                    double alpha, double beta) {
+int launch_short_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                    double* y, double alpha, double beta) {
     auto kern = sweep_short_kernel<K, P>;
     static thread_local size_t configured = 0;
-    if (c.smem > 48 * 1024 && c.smem > configured) {
-        GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        configured = c.smem;
-    }
-    kern<<<c.ntiles, 256, c.smem, pl.stream>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, pl.dense[P]->p,
-                                                (int)pl.S.kD, dir.A);
+    GSG_TRY(ensure_smem(kern, c.smem, configured));
+    kern<<<c.ntiles, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, pl.dense[P]->p, (int)pl.S.kD,
+                                         (int)pl.S.kDp, dir.A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_check("sweep_short", K, c);
 }
 
 template <int K>
-int launch_short_k(gsg_plan& pl, const Direction& dir, const SweepClass& c, const double* x, double* y,
-                   double alpha, double beta) {
-    switch (c.p) {
-        case 0: return launch_short_kp<K, 0>(pl, dir, c, x, y, alpha, beta);
-        case 1: if constexpr ((K << 1) <= SHORT_MAX_NP) return launch_short_kp<K, 1>(pl, dir, c, x, y, alpha, beta); break;
-        case 2: if constexpr ((K << 2) <= SHORT_MAX_NP) return launch_short_kp<K, 2>(pl, dir, c, x, y, alpha, beta); break;
-        case 3: if constexpr ((K << 3) <= SHORT_MAX_NP) return launch_short_kp<K, 3>(pl, dir, c, x, y, alpha, beta); break;
+int launch_short_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                   double* y, double alpha, double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        switch (c.p) {
+            case 0: return launch_short_kp<K, 0>(pl, st, dir, c, x, y, alpha, beta);
+            case 1: if constexpr ((K << 1) <= SHORT_MAX_NP) return launch_short_kp<K, 1>(pl, st, dir, c, x, y, alpha, beta); break;
+            case 2: if constexpr ((K << 2) <= SHORT_MAX_NP) return launch_short_kp<K, 2>(pl, st, dir, c, x, y, alpha, beta); break;
+            case 3: if constexpr ((K << 3) <= SHORT_MAX_NP) return launch_short_kp<K, 3>(pl, st, dir, c, x, y, alpha, beta); break;
+        }
     }
     return fail(GSG_ERR_UNSUPPORTED, "internal: short class not instantiated");
 }
 
 template <int K>
-int launch_generic_k(gsg_plan& pl, const Direction& dir, const SweepClass& c, const double* x, double* y,
-                     double alpha, double beta) {
+int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                  double* y, double alpha, double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        auto kern = sweep_long_kernel<K>;
+        static thread_local size_t configured = 0;
+        GSG_TRY(ensure_smem(kern, c.smem, configured));
+        Bcsr M{pl.b_rowptr.p, pl.b_col.p, pl.b_val.p, pl.KK2};
+        const int* tab = pl.ptab[c.p]->p;
+        kern<<<c.ntiles, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p, M, tab,
+                                                       tab + c.nwarps + 1, c.p, (int)pl.S.kDp, dir.A);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return launch_check("sweep_long", K, c);
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: long kernel not instantiated");
+}
+
+template <int K>
+int launch_generic_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                     double* y, double alpha, double beta) {
     auto kern = sweep_generic_kernel<K>;
     static thread_local size_t configured = 0;
-    if (c.smem > 48 * 1024 && c.smem > configured) {
-        GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        configured = c.smem;
-    }
+    GSG_TRY(ensure_smem(kern, c.smem, configured));
     Bcsr M{pl.b_rowptr.p, pl.b_col.p, pl.b_val.p, pl.KK2};
-    kern<<<c.ntiles, 256, c.smem, pl.stream>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, M, pl.S.k, c.p,
-                                                (int)pl.S.kD, dir.A, c.NPOLE, c.Amin);
+    kern<<<c.ntiles, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, M, pl.S.k, c.p, (int)pl.S.kDp,
+                                         dir.A, c.NPOLE, c.Amin);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_check("sweep_generic", K, c);
 }
 
-// y = alpha * D_d x + beta * y   (d 0-based); x and y must not alias
-int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y) {
-    const Direction& dir = pl.dirs[d];
-    const int K = pl.S.k;
-    for (const SweepClass& c : dir.classes) {
-        int rc;
-        if (c.is_short) {
-            switch (K) {
-                case 1: rc = launch_short_k<1>(pl, dir, c, x, y, alpha, beta); break;
-                case 2: rc = launch_short_k<2>(pl, dir, c, x, y, alpha, beta); break;
-                case 3: rc = launch_short_k<3>(pl, dir, c, x, y, alpha, beta); break;
-                case 4: rc = launch_short_k<4>(pl, dir, c, x, y, alpha, beta); break;
-                case 5: rc = launch_short_k<5>(pl, dir, c, x, y, alpha, beta); break;
-                default: rc = fail(GSG_ERR_UNSUPPORTED, "short kernel: k > 5");
-            }
-        } else {
-            switch (K) {
-                case 1: rc = launch_generic_k<1>(pl, dir, c, x, y, alpha, beta); break;
-                case 2: rc = launch_generic_k<2>(pl, dir, c, x, y, alpha, beta); break;
-                case 3: rc = launch_generic_k<3>(pl, dir, c, x, y, alpha, beta); break;
-                case 4: rc = launch_generic_k<4>(pl, dir, c, x, y, alpha, beta); break;
-                case 5: rc = launch_generic_k<5>(pl, dir, c, x, y, alpha, beta); break;
-                default: rc = launch_generic_k<0>(pl, dir, c, x, y, alpha, beta); break;
-            }
-        }
-        if (rc) return rc;
+#define GSG_K_SWITCH(FN, ...)                       \
+    switch (K) {                                    \
+        case 1: return FN<1>(__VA_ARGS__);          \
+        case 2: return FN<2>(__VA_ARGS__);          \
+        case 3: return FN<3>(__VA_ARGS__);          \
+        case 4: return FN<4>(__VA_ARGS__);          \
+        case 5: return FN<5>(__VA_ARGS__);          \
+        default: break;                             \
     }
-    return 0;
+
+int launch_class(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                 double* y, double alpha, double beta) {
+    const int K = pl.S.k;
+    switch (c.kind) {
+        case Kind::SHORT_TMA: GSG_K_SWITCH(launch_short_tma, pl, st, dir, c, x, y, alpha, beta); break;
+        case Kind::SHORT: GSG_K_SWITCH(launch_short_k, pl, st, dir, c, x, y, alpha, beta); break;
+        case Kind::LONG: GSG_K_SWITCH(launch_long_k, pl, st, dir, c, x, y, alpha, beta); break;
+        case Kind::GENERIC:
+            GSG_K_SWITCH(launch_generic_k, pl, st, dir, c, x, y, alpha, beta);
+            return launch_generic_k<0>(pl, st, dir, c, x, y, alpha, beta);
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: no kernel for this class");
 }
 
 int elementwise_grid(const gsg_plan& pl, int64_t N) {
     const int64_t want = (N + 255) / 256;
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)pl.sm_count * 16));
+}
+
+// y = alpha * D_d x + beta * y   (d 0-based; device layout); x and y must not alias.  The launches
+// of one sweep write disjoint parts of y, so they are forked onto auxiliary streams and joined.
+int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y) {
+    const Direction& dir = pl.dirs[d];
+    const size_t nc = dir.classes.size();
+    if (beta != 0.0 && beta != 1.0) {     // kernels implement beta in {0, 1}
+        scale_kernel<<<elementwise_grid(pl, pl.S.Npad), 256, 0, pl.stream>>>(pl.S.Npad, y, beta);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        beta = 1.0;
+    }
+    const bool fork = nc > 1 && !getenv("GSG_NO_FORK");
+    if (fork) {
+        GSG_CUDA(cudaEventRecord(pl.ev_fork, pl.stream));
+        for (size_t i = 1; i < nc; ++i) GSG_CUDA(cudaStreamWaitEvent(pl.aux[i], pl.ev_fork, 0));
+    }
+    // forked launches first: the long-pole CTAs should be resident before the persistent
+    // streaming kernel occupies every SM
+    for (size_t i = 1; i < nc; ++i) {
+        cudaStream_t st = fork ? pl.aux[i] : pl.stream;
+        GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
+    }
+    if (nc > 0) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    if (fork) {
+        for (size_t i = 1; i < nc; ++i) {
+            GSG_CUDA(cudaEventRecord(pl.ev_done[i], pl.aux[i]));
+            GSG_CUDA(cudaStreamWaitEvent(pl.stream, pl.ev_done[i], 0));
+        }
+    }
+    return 0;
 }
 
 // k = -sum_d a_d D_d w
@@ -430,6 +649,29 @@ int check_plan(const gsg_plan* p) {
     return 0;
 }
 
+// reference vector layout <-> device layout (multi-cells padded from kD to kDp doubles)
+int copy_in(gsg_plan& pl, double* dev, const double* src, cudaMemcpyKind kind) {
+    const gsg::IndexSet& S = pl.S;
+    if (S.kD == S.kDp) {
+        GSG_CUDA(cudaMemcpyAsync(dev, src, (size_t)S.N * sizeof(double), kind, pl.stream));
+    } else {
+        GSG_CUDA(cudaMemcpy2DAsync(dev, (size_t)S.kDp * sizeof(double), src, (size_t)S.kD * sizeof(double),
+                                   (size_t)S.kD * sizeof(double), (size_t)S.ncells_total, kind, pl.stream));
+    }
+    return 0;
+}
+
+int copy_out(gsg_plan& pl, double* dst, const double* dev, cudaMemcpyKind kind) {
+    const gsg::IndexSet& S = pl.S;
+    if (S.kD == S.kDp) {
+        GSG_CUDA(cudaMemcpyAsync(dst, dev, (size_t)S.N * sizeof(double), kind, pl.stream));
+    } else {
+        GSG_CUDA(cudaMemcpy2DAsync(dst, (size_t)S.kD * sizeof(double), dev, (size_t)S.kDp * sizeof(double),
+                                   (size_t)S.kD * sizeof(double), (size_t)S.ncells_total, kind, pl.stream));
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -437,7 +679,7 @@ int check_plan(const gsg_plan* p) {
 // ==========================================================================================
 extern "C" {
 
-int gsg_version(void) { return 100; }
+int gsg_version(void) { return 101; }
 
 const char* gsg_last_error(void) { return g_err.c_str(); }
 
@@ -545,6 +787,13 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     P->sm_count = prop.multiProcessorCount;
     GSG_CUDA(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
     P->stream = P->own_stream;
+    GSG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    P->aux.assign(n + 3, nullptr);
+    P->ev_done.assign(n + 3, nullptr);
+    for (int i = 0; i < n + 3; ++i) {
+        GSG_CUDA(cudaStreamCreateWithFlags(&P->aux[i], cudaStreamNonBlocking));
+        GSG_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
+    }
     GSG_TRY(build_matrix(*P, H_n, H_colptr, H_rowval, H_nzval));
     P->dirs.resize(D);
     for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d));
@@ -554,7 +803,7 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     std::vector<long long> off;
     for (const gsg::Block& b : P->S.blocks) {
         for (int i = 0; i < D; ++i) lv.push_back((unsigned char)b.level[i]);
-        off.push_back(b.offset);
+        off.push_back(b.poffset);
     }
     GSG_TRY(P->r_level.upload(lv));
     GSG_TRY(P->r_offset.upload(off));
@@ -571,10 +820,11 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
 int gsg_plan_destroy(gsg_plan* plan) {
     if (!plan) return 0;
     cudaSetDevice(plan->device);
-    if (plan->own_stream) {
-        cudaStreamSynchronize(plan->own_stream);
-        cudaStreamDestroy(plan->own_stream);
-    }
+    cudaDeviceSynchronize();
+    for (cudaStream_t st : plan->aux) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : plan->ev_done) if (ev) cudaEventDestroy(ev);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     delete plan;
     return 0;
 }
@@ -582,6 +832,12 @@ int gsg_plan_destroy(gsg_plan* plan) {
 int gsg_plan_size(const gsg_plan* plan, int64_t* size_out) {
     if (!plan || !size_out) return fail(GSG_ERR_ARG, "null pointer");
     *size_out = plan->S.N;
+    return 0;
+}
+
+int gsg_plan_dev_size(const gsg_plan* plan, int64_t* size_out) {
+    if (!plan || !size_out) return fail(GSG_ERR_ARG, "null pointer");
+    *size_out = plan->S.Npad;
     return 0;
 }
 
@@ -597,7 +853,32 @@ int gsg_plan_sync(gsg_plan* plan) {
     return 0;
 }
 
-// ---- device-pointer operator apply ----------------------------------------------------------------
+int gsg_pack_dev(gsg_plan* plan, const double* ref_layout_dev, double* dev_layout_dev) {
+    GSG_TRY(check_plan(plan));
+    if (!ref_layout_dev || !dev_layout_dev) return fail(GSG_ERR_ARG, "null pointer");
+    return copy_in(*plan, dev_layout_dev, ref_layout_dev, cudaMemcpyDeviceToDevice);
+}
+
+int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_layout_dev) {
+    GSG_TRY(check_plan(plan));
+    if (!ref_layout_dev || !dev_layout_dev) return fail(GSG_ERR_ARG, "null pointer");
+    return copy_out(*plan, ref_layout_dev, dev_layout_dev, cudaMemcpyDeviceToDevice);
+}
+
+// development aid: enable (n > 0) / read back the per-phase clock stamps of the TMA kernel's CTA 0
+int gsg_debug_stamps(gsg_plan* plan, long long* out, int n) {
+    GSG_TRY(check_plan(plan));
+    if (!plan->dbg) {
+        GSG_TRY(plan->dbgbuf.resize(64 * 8));
+        plan->dbg = plan->dbgbuf.p;
+        return 0;
+    }
+    GSG_CUDA(cudaDeviceSynchronize());
+    if (out && n > 0) GSG_CUDA(cudaMemcpy(out, plan->dbg, sizeof(long long) * std::min(n, 64 * 8), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- device-pointer operator apply (device layout) ------------------------------------------------
 int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, double beta, double* y_dev) {
     GSG_TRY(check_plan(plan));
     if (d < 1 || d > plan->S.D) return fail(GSG_ERR_ARG, "axis d out of range [1,D]");
@@ -620,16 +901,14 @@ int gsg_apply_laplacian_dev(gsg_plan* plan, const double* x_dev, double* y_dev, 
 
 // ---- host-pointer operator apply ------------------------------------------------------------------
 static int stage_in(gsg_plan* plan, const double* x) {
-    const size_t N = (size_t)plan->S.N;
-    GSG_TRY(plan->wx.resize(N));
-    GSG_TRY(plan->wy.resize(N));
-    GSG_CUDA(cudaMemcpyAsync(plan->wx.p, x, N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
-    return 0;
+    const size_t Np = (size_t)plan->S.Npad;
+    GSG_TRY(plan->wx.resize(Np));
+    GSG_TRY(plan->wy.resize(Np));
+    return copy_in(*plan, plan->wx.p, x, cudaMemcpyHostToDevice);
 }
 
 static int stage_out(gsg_plan* plan, double* y) {
-    const size_t N = (size_t)plan->S.N;
-    GSG_CUDA(cudaMemcpyAsync(y, plan->wy.p, N * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    GSG_TRY(copy_out(*plan, y, plan->wy.p, cudaMemcpyDeviceToHost));
     GSG_CUDA(cudaStreamSynchronize(plan->stream));
     return 0;
 }
@@ -655,7 +934,7 @@ int gsg_apply_laplacian(gsg_plan* plan, const double* x, double* y) {
     GSG_TRY(check_plan(plan));
     if (!x || !y) return fail(GSG_ERR_ARG, "null pointer");
     GSG_TRY(stage_in(plan, x));
-    GSG_TRY(plan->wtmp.resize((size_t)plan->S.N));
+    GSG_TRY(plan->wtmp.resize((size_t)plan->S.Npad));
     GSG_TRY(laplacian(*plan, plan->wx.p, plan->wy.p, plan->wtmp.p));
     return stage_out(plan, y);
 }
@@ -666,18 +945,17 @@ int gsg_rk4_advect_dev(gsg_plan* plan, const double* a, double* y_dev, double dt
     if (!a || !y_dev || nsteps < 0) return fail(GSG_ERR_ARG, "bad argument");
     std::vector<double> av(a, a + plan->S.D);
     gsg_plan& pl = *plan;
-    return rk4_loop(pl, plan->S.N, y_dev, dt, nsteps,
+    return rk4_loop(pl, plan->S.Npad, y_dev, dt, nsteps,
                     [&](const double* w, double* k) { return advect_rhs(pl, av.data(), w, k); });
 }
 
 int gsg_rk4_advect(gsg_plan* plan, const double* a, double* y, double dt, int64_t nsteps) {
     GSG_TRY(check_plan(plan));
     if (!a || !y || nsteps < 0) return fail(GSG_ERR_ARG, "bad argument");
-    const size_t N = (size_t)plan->S.N;
-    GSG_TRY(plan->wx.resize(N));
-    GSG_CUDA(cudaMemcpyAsync(plan->wx.p, y, N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+    GSG_TRY(plan->wx.resize((size_t)plan->S.Npad));
+    GSG_TRY(copy_in(*plan, plan->wx.p, y, cudaMemcpyHostToDevice));
     GSG_TRY(gsg_rk4_advect_dev(plan, a, plan->wx.p, dt, nsteps));
-    GSG_CUDA(cudaMemcpyAsync(y, plan->wx.p, N * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    GSG_TRY(copy_out(*plan, y, plan->wx.p, cudaMemcpyDeviceToHost));
     GSG_CUDA(cudaStreamSynchronize(plan->stream));
     return 0;
 }
@@ -686,36 +964,36 @@ int gsg_rk4_wave_dev(gsg_plan* plan, double* u_dev, double* v_dev, double dt, in
     GSG_TRY(check_plan(plan));
     if (!u_dev || !v_dev || nsteps < 0) return fail(GSG_ERR_ARG, "bad argument");
     gsg_plan& pl = *plan;
-    const int64_t N = pl.S.N;
+    const int64_t Np = pl.S.Npad;
     // state y = [u; v] kept contiguous in a workspace so the stage kernels see one vector
-    GSG_TRY(pl.wy.resize(2 * (size_t)N));
-    GSG_TRY(pl.wtmp.resize((size_t)N));
+    GSG_TRY(pl.wy.resize(2 * (size_t)Np));
+    GSG_TRY(pl.wtmp.resize((size_t)Np));
     double* y = pl.wy.p;
-    GSG_CUDA(cudaMemcpyAsync(y, u_dev, N * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
-    GSG_CUDA(cudaMemcpyAsync(y + N, v_dev, N * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
-    int rc = rk4_loop(pl, 2 * N, y, dt, nsteps, [&](const double* w, double* k) {
+    GSG_CUDA(cudaMemcpyAsync(y, u_dev, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
+    GSG_CUDA(cudaMemcpyAsync(y + Np, v_dev, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
+    int rc = rk4_loop(pl, 2 * Np, y, dt, nsteps, [&](const double* w, double* k) {
         // [u; v]' = [v; L u]   (src/pdes.jl:22-49)
-        GSG_CUDA(cudaMemcpyAsync(k, w + N, N * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
-        return laplacian(pl, w, k + N, pl.wtmp.p);
+        GSG_CUDA(cudaMemcpyAsync(k, w + Np, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
+        return laplacian(pl, w, k + Np, pl.wtmp.p);
     });
     if (rc) return rc;
-    GSG_CUDA(cudaMemcpyAsync(u_dev, y, N * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
-    GSG_CUDA(cudaMemcpyAsync(v_dev, y + N, N * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
+    GSG_CUDA(cudaMemcpyAsync(u_dev, y, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
+    GSG_CUDA(cudaMemcpyAsync(v_dev, y + Np, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
     return 0;
 }
 
 int gsg_rk4_wave(gsg_plan* plan, double* u, double* v, double dt, int64_t nsteps) {
     GSG_TRY(check_plan(plan));
     if (!u || !v || nsteps < 0) return fail(GSG_ERR_ARG, "bad argument");
-    const size_t N = (size_t)plan->S.N;
-    GSG_TRY(plan->wx.resize(2 * N));
+    const size_t Np = (size_t)plan->S.Npad;
+    GSG_TRY(plan->wx.resize(2 * Np));
     double* du = plan->wx.p;
-    double* dv = plan->wx.p + N;
-    GSG_CUDA(cudaMemcpyAsync(du, u, N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
-    GSG_CUDA(cudaMemcpyAsync(dv, v, N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
+    double* dv = plan->wx.p + Np;
+    GSG_TRY(copy_in(*plan, du, u, cudaMemcpyHostToDevice));
+    GSG_TRY(copy_in(*plan, dv, v, cudaMemcpyHostToDevice));
     GSG_TRY(gsg_rk4_wave_dev(plan, du, dv, dt, nsteps));
-    GSG_CUDA(cudaMemcpyAsync(u, du, N * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
-    GSG_CUDA(cudaMemcpyAsync(v, dv, N * sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    GSG_TRY(copy_out(*plan, u, du, cudaMemcpyDeviceToHost));
+    GSG_TRY(copy_out(*plan, v, dv, cudaMemcpyDeviceToHost));
     GSG_CUDA(cudaStreamSynchronize(plan->stream));
     return 0;
 }
@@ -724,18 +1002,19 @@ int gsg_energy(gsg_plan* plan, const double* u, const double* udot, double* ener
     GSG_TRY(check_plan(plan));
     if (!u || !udot || !energy_out) return fail(GSG_ERR_ARG, "null pointer");
     gsg_plan& pl = *plan;
-    const size_t N = (size_t)pl.S.N;
-    GSG_TRY(pl.wx.resize(N));
-    GSG_TRY(pl.wy.resize(N));
+    const size_t Np = (size_t)pl.S.Npad;
+    GSG_TRY(pl.wx.resize(Np));
+    GSG_TRY(pl.wy.resize(Np));
     GSG_TRY(pl.wred.resize(1));
     GSG_CUDA(cudaMemsetAsync(pl.wred.p, 0, sizeof(double), pl.stream));
-    const int grid = elementwise_grid(pl, (int64_t)N);
-    GSG_CUDA(cudaMemcpyAsync(pl.wx.p, udot, N * sizeof(double), cudaMemcpyHostToDevice, pl.stream));
-    sumsq_kernel<<<grid, 256, 0, pl.stream>>>((long long)N, pl.wx.p, pl.wred.p);
-    GSG_CUDA(cudaMemcpyAsync(pl.wx.p, u, N * sizeof(double), cudaMemcpyHostToDevice, pl.stream));
+    const int grid = elementwise_grid(pl, (int64_t)Np);
+    // padding slots are zero (zero-filled allocation, never written), so they add nothing
+    GSG_TRY(copy_in(pl, pl.wx.p, udot, cudaMemcpyHostToDevice));
+    sumsq_kernel<<<grid, 256, 0, pl.stream>>>((long long)Np, pl.wx.p, pl.wred.p);
+    GSG_TRY(copy_in(pl, pl.wx.p, u, cudaMemcpyHostToDevice));
     for (int d = 0; d < pl.S.D; ++d) {
         GSG_TRY(sweep(pl, d, 1.0, pl.wx.p, 0.0, pl.wy.p));
-        sumsq_kernel<<<grid, 256, 0, pl.stream>>>((long long)N, pl.wy.p, pl.wred.p);
+        sumsq_kernel<<<grid, 256, 0, pl.stream>>>((long long)Np, pl.wy.p, pl.wred.p);
     }
     g_launches.fetch_add(pl.S.D + 1, std::memory_order_relaxed);
     GSG_CUDA(cudaMemcpyAsync(energy_out, pl.wred.p, sizeof(double), cudaMemcpyDeviceToHost, pl.stream));
@@ -760,6 +1039,7 @@ int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double*
     T.k = pl.S.k;
     T.n = pl.S.n;
     T.KD = (int)pl.S.kD;
+    T.KDp = (int)pl.S.kDp;
     T.legw = 2 * (gsg::K_MAX + 1);
     const int nwarp = 8;
     const size_t per_warp = ((size_t)T.D * (T.n + 1) * T.k + (size_t)T.D * (T.n + 1)) * sizeof(double);
@@ -780,11 +1060,10 @@ int gsg_reconstruct(gsg_plan* plan, const double* vcoeffs, const double* points,
     if (!vcoeffs || !points || !out || npts < 0) return fail(GSG_ERR_ARG, "bad argument");
     if (npts == 0) return 0;
     gsg_plan& pl = *plan;
-    const size_t N = (size_t)pl.S.N;
-    GSG_TRY(pl.wx.resize(N));
+    GSG_TRY(pl.wx.resize((size_t)pl.S.Npad));
     GSG_TRY(pl.wpts.resize((size_t)npts * pl.S.D));
     GSG_TRY(pl.wout.resize((size_t)npts));
-    GSG_CUDA(cudaMemcpyAsync(pl.wx.p, vcoeffs, N * sizeof(double), cudaMemcpyHostToDevice, pl.stream));
+    GSG_TRY(copy_in(pl, pl.wx.p, vcoeffs, cudaMemcpyHostToDevice));
     GSG_CUDA(cudaMemcpyAsync(pl.wpts.p, points, (size_t)npts * pl.S.D * sizeof(double), cudaMemcpyHostToDevice, pl.stream));
     GSG_TRY(gsg_reconstruct_dev(plan, pl.wx.p, pl.wpts.p, npts, pl.wout.p));
     GSG_CUDA(cudaMemcpyAsync(out, pl.wout.p, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, pl.stream));

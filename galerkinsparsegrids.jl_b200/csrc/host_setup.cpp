@@ -404,8 +404,10 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
     by_level.clear();
     kD = 1;
     for (int i = 0; i < D; ++i) kD *= k;
+    kDp = (kD + 1) & ~int64_t(1);
     std::vector<int> lv(D, 0);
-    int64_t off = 0;
+    int64_t off = 0, poff = 0;
+    ncells_total = 0;
     while (true) {
         int sum = 0;
         for (int i = 0; i < D; ++i) sum += lv[i];
@@ -419,7 +421,10 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
                 b.ncells *= b.cells[i];
             }
             b.offset = off;
+            b.poffset = poff;
             off += b.ncells * kD;
+            poff += b.ncells * kDp;
+            ncells_total += b.ncells;
             by_level[lv] = (int)blocks.size();
             blocks.push_back(std::move(b));
         }
@@ -428,6 +433,7 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
         if (i == D) break;
     }
     N = off;
+    Npad = poff;
     return true;
 }
 

@@ -42,13 +42,16 @@ Csc transpose(const Csc& A);
 struct Block {
     std::vector<int> level;     // 0-based levels, size D
     std::vector<int> cells;     // cells per dim: 1 << max(0, level-1)
-    int64_t offset = 0;         // offset of the block in the state vector
+    int64_t offset = 0;         // offset of the block in the reference vector layout
+    int64_t poffset = 0;        // offset in the device-internal layout (cells padded to kDp)
     int64_t ncells = 0;
 };
 
 struct IndexSet {               // src/dg_vmethods.jl:35-142 (the D2V / V2Dref loop order)
     int D = 0, k = 0, n = 0, scheme = 0;
     int64_t N = 0, kD = 0;
+    int64_t kDp = 0, Npad = 0;  // device layout: every k^D multi-cell padded to an even length
+    int64_t ncells_total = 0;   // (16-byte alignment for TMA bulk copies and 128-bit accesses)
     std::vector<Block> blocks;
     std::map<std::vector<int>, int> by_level;
     bool build(int D, int k, int n, int scheme);

@@ -8,8 +8,11 @@
 // multiplied by the principal sub-block M[0:N', 0:N'] of the 1-D matrix
 // (src/multidim_derivative.jl:30-55).  Inside a group an ITEM r fixes the
 // other dims' cells; for every 1-D cell q the item owns one contiguous multi-cell of KD = K^D
-// doubles at  base[level(q)] + KD * (lo + S * (c(q) + C(level(q)) * hi)),  r = lo + S * hi.
+// doubles at  base[level(q)] + KDp * (lo + S * (c(q) + C(level(q)) * hi)),  r = lo + S * hi.
 // Within a multi-cell the entry (a, m_d, b) sits at  a + A*m_d + K*A*b  with A = K^(d-1).
+// DEVICE LAYOUT: identical to the reference's vector layout (src/dg_vmethods.jl:48-73) except
+// that every multi-cell is padded from KD to KDp = KD rounded up to even, so that every cell
+// starts on a 16-byte boundary (TMA bulk copies, 128-bit accesses).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,11 +49,12 @@ __device__ __forceinline__ void q_decode(int q, int& ld, int& cd, int& Cd) {
     Cd = ld <= 1 ? 1 : 1 << (ld - 1);
 }
 
-__device__ __forceinline__ long long cell_addr(const long long* base, int S, int q, int r, int KD) {
+// KDp = padded multi-cell stride of the device layout (K^D rounded up to even)
+__device__ __forceinline__ long long cell_addr(const long long* base, int S, int q, int r, int KDp) {
     int ld, cd, Cd;
     q_decode(q, ld, cd, Cd);
     const int lo = r % S, hi = r / S;
-    return base[ld] + (long long)KD * (lo + (long long)S * (cd + (long long)Cd * hi));
+    return base[ld] + (long long)KDp * (lo + (long long)S * (cd + (long long)Cd * hi));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -62,7 +66,7 @@ template <int K, int P>
 __global__ void __launch_bounds__(256)
 sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
                    const GroupDev* __restrict__ groups, const TileDev* __restrict__ tiles,
-                   const double* __restrict__ Mdense, int KD, int A) {
+                   const double* __restrict__ Mdense, int KD, int KDp, int A) {
     constexpr int NQ = 1 << P, NP = K * NQ;
     extern __shared__ __align__(16) double smem[];
     double* Hs = smem;                                   // NP*NP (padded to even)
@@ -84,7 +88,7 @@ sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     // ---- stage in: one warp per multi-cell, lanes stride the KD contiguous doubles
     for (int c = warp; c < ncell; c += nwarp) {
         const int q = c / nr, r = c - q * nr;
-        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KD);
+        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KDp);
         double* dst = xs + (size_t)c * KD;
         int e = lane;
         for (; e + 96 < KD; e += 128) {
@@ -124,7 +128,7 @@ sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     // ---- stage out with the epilogue y = alpha*Mx + beta*y
     for (int c = warp; c < ncell; c += nwarp) {
         const int q = c / nr, r = c - q * nr;
-        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KD);
+        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
         const double* srcs = xs + (size_t)c * KD;
         if (beta == 0.0) {
             for (int e = lane; e < KD; e += 32) dstg[e] = alpha * srcs[e];
@@ -143,6 +147,266 @@ sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
 }
 
 // ------------------------------------------------------------------------------------------
+// Short poles, Blackwell-native path: ONE persistent, warp-specialised kernel for all short
+// classes of a sweep.  Warp 0 is the TMA producer: it streams tiles (CT multi-cells each, every
+// cell one contiguous 16-byte-aligned run) into an NS-deep shared-memory ring with
+// cp.async.bulk + mbarrier complete_tx, and streams finished tiles back with bulk stores -- or,
+// for y += alpha*D_d x, with cp.reduce.async.bulk.add.f64 so y is never loaded into the SM.
+// The 8 compute warps wait on the tile's `full` barrier, own one pole per thread (registers),
+// multiply by the dense N' x N' block (broadcast shared-memory loads), write alpha*result in
+// place, fence to the async proxy and arrive on the tile's `done` barrier.
+// ------------------------------------------------------------------------------------------
+struct TileS {                // self-contained: the producer never touches the group table
+    long long base[4];        // block offsets for level_d = 0..3 (register-resident classes: P <= 3)
+    int S;                    // prod of cells of dims < d
+    int r0;
+    short nr;
+    short P;
+    int pad;
+};
+
+struct ShortParams {
+    int KD, KDp, A;
+    int stage_doubles;  // doubles per ring stage
+    int nstage;
+};
+
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_red_add_f64(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+// Dense principal sub-blocks of the 1-D matrix for the register-resident classes, passed as a
+// __grid_constant__ kernel parameter: the fully unrolled DFMAs read H as immediate constant-bank
+// operands (c[0][imm]), so the matrix costs neither shared-memory bandwidth nor registers.
+template <int K>
+struct ShortDims {
+    __host__ __device__ static constexpr int pmax() {
+        int p = 0;
+        while (p < 3 && (K << (p + 1)) <= 32) ++p;
+        return p;
+    }
+    __host__ __device__ static constexpr int hoff(int P) {          // offset of class P's block (each padded to even)
+        int o = 0;
+        for (int p = 0; p < P; ++p) o += (((K << p) * (K << p)) + 1) & ~1;
+        return o;
+    }
+    __host__ __device__ static constexpr int htotal() { return hoff(pmax() + 1); }
+};
+
+template <int K>
+struct HDense {
+    double v[ShortDims<K>::htotal()];
+};
+
+// One pole per thread: x[N'] in registers, rows accumulated RC at a time (RC independent DFMA
+// chains), results alpha*acc written back in place.
+template <int K, int P>
+__device__ __forceinline__ void short_tile_compute(double* xs, const HDense<K>& hd, int nr, int KDp, int A, int PI,
+                                                   const int* pole_off, double alpha, int ctid, int ncth) {
+    constexpr int NQ = 1 << P, NP = K * NQ;
+    constexpr int RC = NP < 12 ? NP : 12;        // rows per accumulation chunk
+    constexpr int HO = ShortDims<K>::hoff(P);
+    const size_t qstride = (size_t)nr * KDp;
+    for (int r = 0; r < nr; ++r) {
+        for (int j = ctid; j < PI; j += ncth) {
+            double* pole = xs + (size_t)r * KDp + pole_off[j];
+            double x[NP];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int m = 0; m < K; ++m) x[q * K + m] = pole[q * qstride + A * m];
+#pragma unroll
+            for (int i0 = 0; i0 < NP; i0 += RC) {
+                double acc[RC];
+#pragma unroll
+                for (int i = 0; i < RC; ++i) acc[i] = 0.0;
+#pragma unroll
+                for (int jx = 0; jx < NP; ++jx)
+#pragma unroll
+                    for (int i = 0; i < RC; ++i)
+                        if (i0 + i < NP) acc[i] = fma(hd.v[HO + (i0 + i) * NP + jx], x[jx], acc[i]);
+#pragma unroll
+                for (int i = 0; i < RC; ++i)
+                    if (i0 + i < NP) {
+                        const int q = (i0 + i) / K, m = (i0 + i) % K;
+                        pole[q * qstride + A * m] = alpha * acc[i];
+                    }
+            }
+        }
+    }
+}
+
+constexpr int SHORT_TMA_COMPUTE_WARPS = 8;
+
+// producer side (whole warp 0): lane q moves the multi-cells of 1-D cell q, one bulk copy per run
+// of memory-contiguous items (items are contiguous while lo = r % S does not wrap).
+__device__ __forceinline__ void short_tma_load(const double* __restrict__ X, const TileS& t, double* dst, unsigned bar,
+                                               int KDp, int lane) {
+    const int NQ = 1 << t.P, S = t.S, nr = t.nr;
+    if (lane == 0) tma::mbar_expect_tx(bar, (unsigned)(NQ * nr * KDp * 8));
+    __syncwarp();
+    if (lane < NQ) {
+        const int q = lane;
+        int r = 0;
+        while (r < nr) {
+            const int lo = (t.r0 + r) % S;
+            const int run = min(nr - r, S - lo);
+            const double* src = X + cell_addr(t.base, S, q, t.r0 + r, KDp);
+            tma::bulk_g2s(tma::smem_u32(dst + (size_t)(q * nr + r) * KDp), src, (unsigned)(run * KDp * 8), bar);
+            r += run;
+        }
+    }
+}
+
+__device__ __forceinline__ void short_tma_store(double* __restrict__ Y, const TileS& t, const double* srcs, int KDp,
+                                                int lane, int accumulate) {
+    const int NQ = 1 << t.P, S = t.S, nr = t.nr;
+    if (lane < NQ) {
+        const int q = lane;
+        int r = 0;
+        while (r < nr) {
+            const int lo = (t.r0 + r) % S;
+            const int run = min(nr - r, S - lo);
+            double* dstg = Y + cell_addr(t.base, S, q, t.r0 + r, KDp);
+            const unsigned sa = tma::smem_u32(srcs + (size_t)(q * nr + r) * KDp);
+            if (accumulate) tma::bulk_red_add_f64(dstg, sa, (unsigned)(run * KDp * 8));
+            else tma::bulk_s2g(dstg, sa, (unsigned)(run * KDp * 8));
+            r += run;
+        }
+    }
+    tma::bulk_commit();
+}
+
+template <int K>
+__global__ void __launch_bounds__(32 * (SHORT_TMA_COMPUTE_WARPS + 1), 1)
+sweep_short_tma_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+                       const GroupDev* __restrict__ groups, const TileS* __restrict__ tiles, int ntiles,
+                       const __grid_constant__ HDense<K> hd, const ShortParams prm,
+                       long long* __restrict__ dbg) {   // dbg: optional per-phase clock stamps (CTA 0)
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);     // full[NS], done[NS]
+    const int PI = prm.KD / K;
+    int* pole_off = reinterpret_cast<int*>(smraw + 128);
+    size_t off = 128 + (size_t)PI * 4;
+    off = (off + 127) & ~(size_t)127;
+    double* ring = reinterpret_cast<double*>(smraw + off);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NS = prm.nstage;
+    const int KDp = prm.KDp;
+    const int count = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    for (int j = tid; j < PI; j += blockDim.x) {
+        const int b = j / prm.A, a = j - b * prm.A;
+        pole_off[j] = a + K * prm.A * b;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            tma::mbar_init(tma::smem_u32(&bars[s]), 1);
+            tma::mbar_init(tma::smem_u32(&bars[NS + s]), SHORT_TMA_COMPUTE_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= TMA producer / storer (warp 0, lanes = 1-D cells) =================
+        const int pre = min(NS, count);
+        for (int it = 0; it < pre; ++it) {
+            const TileS t = tiles[blockIdx.x + (long long)it * gridDim.x];
+            short_tma_load(X, t, ring + (size_t)(it % NS) * prm.stage_doubles, tma::smem_u32(&bars[it % NS]), KDp, lane);
+        }
+        TileS tcur = count > 0 ? tiles[blockIdx.x] : TileS{};
+        for (int it = 0; it < count; ++it) {
+            const int s = it % NS;
+            const unsigned ph = (unsigned)((it / NS) & 1);
+            // prefetch the descriptors needed next while waiting for the compute warps
+            TileS tnext = tcur, tload = tcur;
+            if (it + 1 < count) tnext = tiles[blockIdx.x + (long long)(it + 1) * gridDim.x];
+            if (it + NS < count) tload = tiles[blockIdx.x + (long long)(it + NS) * gridDim.x];
+            const long long c0 = clock64();
+            tma::mbar_wait(tma::smem_u32(&bars[NS + s]), ph);          // tile computed
+            const long long c1 = clock64();
+            short_tma_store(Y, tcur, ring + (size_t)s * prm.stage_doubles, KDp, lane, accumulate);
+            const long long c2 = clock64();
+            long long c3 = c2;
+            if (it + NS < count) {
+                tma::bulk_wait_read0();        // the stage may be overwritten once its stores have read it
+                __syncwarp();
+                c3 = clock64();
+                short_tma_load(X, tload, ring + (size_t)s * prm.stage_doubles, tma::smem_u32(&bars[s]), KDp, lane);
+            }
+            if (dbg && blockIdx.x == 0 && it < 64 && lane == 0) {
+                dbg[it * 8 + 0] = c0; dbg[it * 8 + 1] = c1; dbg[it * 8 + 2] = c2; dbg[it * 8 + 3] = c3;
+                dbg[it * 8 + 4] = clock64();
+            }
+            tcur = tnext;
+        }
+        tma::bulk_wait0();
+    } else {
+        // ================= compute warps =================
+        const int ctid = tid - 32, ncth = 32 * SHORT_TMA_COMPUTE_WARPS;
+        for (int it = 0; it < count; ++it) {
+            const int s = it % NS;
+            const unsigned ph = (unsigned)((it / NS) & 1);
+            const TileS t = tiles[blockIdx.x + (long long)it * gridDim.x];
+            const long long w0 = clock64();
+            tma::mbar_wait(tma::smem_u32(&bars[s]), ph);
+            const long long w1 = clock64();
+            double* xs = ring + (size_t)s * prm.stage_doubles;
+            switch (t.P) {
+                case 0: short_tile_compute<K, 0>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 1: if constexpr (ShortDims<K>::pmax() >= 1) short_tile_compute<K, 1>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 2: if constexpr (ShortDims<K>::pmax() >= 2) short_tile_compute<K, 2>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 3: if constexpr (ShortDims<K>::pmax() >= 3) short_tile_compute<K, 3>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+            }
+            tma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[NS + s]));
+            if (dbg && blockIdx.x == 0 && it < 64 && ctid == 0) {
+                dbg[it * 8 + 5] = w0; dbg[it * 8 + 6] = w1; dbg[it * 8 + 7] = clock64();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic poles (any p, any K): a tile holds PT = nr * NPOLE poles; x is staged TRANSPOSED in
 // shared memory as xs[row = q*K+m][pole] so that lanes = poles read conflict-free; each thread
 // computes one block-row (K outputs) of one pole from the K x K block-CSR matrix (uniform,
@@ -156,7 +420,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
                      const GroupDev* __restrict__ groups, const TileDev* __restrict__ tiles,
-                     Bcsr M, int krt, int p, int KD, int A, int NPOLE, int Amin) {
+                     Bcsr M, int krt, int p, int KDp, int A, int NPOLE, int Amin) {
     constexpr int KC = K ? K : 10;
     const int kk = K ? K : krt;
     const int NQ = 1 << p, NP = kk * NQ;
@@ -187,7 +451,7 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 
     for (int c = warp; c < ncell; c += nwarp) {
         const int q = c / nr, r = c - q * nr;
-        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KD);
+        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KDp);
         double* dst = xs + (size_t)q * kk * PT + r * NPOLE;
         for (int tt = lane; tt < TL; tt += 32) dst[tab_s[tt]] = src[tab_g[tt]];
     }
@@ -226,7 +490,7 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 
     for (int c = warp; c < ncell; c += nwarp) {
         const int q = c / nr, r = c - q * nr;
-        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KD);
+        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
         const double* srcs = ys + (size_t)q * kk * PT + r * NPOLE;
         if (beta == 0.0) {
             for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * srcs[tab_s[tt]];
@@ -234,6 +498,118 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
             for (int tt = lane; tt < TL; tt += 32) {
                 const int g = tab_g[tt];
                 dstg[g] = fma(alpha, srcs[tab_s[tt]], beta * dstg[g]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Long poles (p >= 4 at k = 3): lanes = poles.  A tile holds PT <= 32 poles (a sub-range
+// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles); the
+// whole x tile sits in shared memory as xs[row][32] (conflict-free for lanes = poles).  The
+// block-rows of the K x K block-CSR matrix are split over the CTA's warps by a host-computed
+// partition balanced in block count; for each block the warp loads the K x K values with
+// uniform (broadcast) 128-bit loads, K x values per lane from shared memory and issues K*K
+// DFMAs.  Each finished block-row (K*PT values) goes through a per-warp scratch so that the
+// global write is coalesced in memory order.
+//   in-item order t -> a = t % na, m = (t / na) % K, bl = t / (K*na):
+//   pole = a + na*bl, in-cell offset = ebase + a + A*m + K*A*bl.
+// ------------------------------------------------------------------------------------------
+struct TileLong {
+    int group;
+    int r0;
+    int ebase;
+    short nr, na, nb, pad;
+};
+
+template <int K>
+__global__ void __launch_bounds__(512)
+sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
+                  const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles, Bcsr M,
+                  const int* __restrict__ wsplit, const int* __restrict__ rowend, int p, int KDp, int A) {
+    constexpr int KK2 = (K * K + 1) & ~1;
+    const int NQ = 1 << p, NP = K * NQ;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ long long sbase[MAXL + 1];
+    __shared__ int sS;
+    __shared__ short tab_row[K * 32];   // m*32 + pole-in-item
+    __shared__ int tab_g[K * 32];       // in-cell offset
+
+    const TileLong t = tiles[blockIdx.x];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
+    const int na = t.na, nb = t.nb, nr = t.nr;
+    const int PIt = na * nb;            // poles per item in this tile
+    const int PT = nr * PIt;            // poles in the tile (<= 32)
+    const int TL = K * PIt;
+    double* xs = smem;                                   // NP * 32
+    double* scratch = smem + (size_t)NP * 32 + (size_t)warp * (K * 32);
+
+    if (tid <= p) sbase[tid] = groups[t.group].base[tid];
+    if (tid == 32) sS = groups[t.group].S;
+    for (int tt = tid; tt < TL; tt += nth) {
+        const int a = tt % na, rest = tt / na;
+        const int m = rest % K, bl = rest / K;
+        tab_row[tt] = (short)(m * 32 + a + na * bl);
+        tab_g[tt] = t.ebase + a + A * m + K * A * bl;
+    }
+    __syncthreads();
+    const int S = sS;
+
+    // ---- stage in
+    const int ncell = NQ * nr;
+    for (int c = warp; c < ncell; c += nwarp) {
+        const int q = c / nr, r = c - q * nr;
+        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KDp);
+        double* dst = xs + (size_t)q * K * 32 + r * PIt;
+        for (int tt = lane; tt < TL; tt += 32) dst[tab_row[tt]] = src[tab_g[tt]];
+    }
+    __syncthreads();
+
+    // ---- block-rows of this warp
+    const int q1 = wsplit[warp + 1];
+    const bool active = lane < PT;
+    for (int q = wsplit[warp]; q < q1; ++q) {
+        double acc[K];
+#pragma unroll
+        for (int m = 0; m < K; ++m) acc[m] = 0.0;
+        const int b1 = rowend[q];        // blocks with column < NQ (principal sub-block), counted loop
+#pragma unroll 2
+        for (int blk = M.rowptr[q]; blk < b1; ++blk) {
+            const int qc = __ldg(M.col + blk);
+            const double2* hv = reinterpret_cast<const double2*>(M.val + (size_t)blk * KK2);
+            double h[KK2];
+#pragma unroll
+            for (int i = 0; i < KK2 / 2; ++i) {
+                const double2 v = __ldg(hv + i);
+                h[2 * i] = v.x;
+                h[2 * i + 1] = v.y;
+            }
+            const double* xv = xs + (size_t)qc * K * 32 + lane;
+            double xr[K];
+#pragma unroll
+            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[mi * 32];
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(h[mo * K + mi], xr[mi], acc[mo]);
+        }
+        __syncwarp();
+        if (active) {
+#pragma unroll
+            for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
+        }
+        __syncwarp();
+        for (int r = 0; r < nr; ++r) {
+            double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
+            const double* sc = scratch + r * PIt;
+            if (beta == 0.0) {
+                for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
+            } else {
+                for (int tt = lane; tt < TL; tt += 32) {
+                    const int g = tab_g[tt];
+                    dstg[g] = fma(alpha, sc[tab_row[tt]], beta * dstg[g]);
+                }
             }
         }
     }
@@ -262,6 +638,11 @@ __global__ void rk_final_kernel(long long N, double* __restrict__ u, const doubl
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
         u[i] = fma(ca, k[i], acc[i]);
+}
+
+__global__ void scale_kernel(long long N, double* __restrict__ y, double beta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) y[i] *= beta;
 }
 
 __global__ void sumsq_kernel(long long N, const double* __restrict__ x, double* __restrict__ out) {
@@ -295,7 +676,7 @@ struct ReconTables {
     const long long* blk_offset;      // nblocks
     const double* leg;                // (KMAX+1) * 2(KMAX+1)
     const double* dg;                 // k * 2k
-    int nblocks, D, k, n, KD, legw;   // legw = 2*(KMAX+1)
+    int nblocks, D, k, n, KD, KDp, legw;   // legw = 2*(KMAX+1); KDp = padded cell stride
 };
 
 __device__ __forceinline__ double poly_eval(const double* __restrict__ v, int half, double x) {
@@ -350,7 +731,7 @@ reconstruct_kernel(ReconTables T, const double* __restrict__ coeffs, const doubl
                 lin += (long long)ci[d * n1 + l] * stride;
                 stride *= (l <= 1) ? 1 : (1LL << (l - 1));
             }
-            const double* cf = coeffs + T.blk_offset[b] + lin * T.KD;
+            const double* cf = coeffs + T.blk_offset[b] + lin * T.KDp;
             for (int e = lane; e < T.KD; e += 32) {
                 int rem = e;
                 double prod = 1.0;

@@ -79,6 +79,13 @@ int gsg_plan_create(int D, int k, int n, int scheme,
                     const double* H_nzval, int device, gsg_plan** plan_out);
 int gsg_plan_destroy(gsg_plan* plan);
 int gsg_plan_size(const gsg_plan* plan, int64_t* size_out);
+/* Device vectors live in the DEVICE LAYOUT: the reference layout with every k^D multi-cell
+ * padded to an even number of doubles (16-byte aligned cells for TMA bulk copies).  dev_size
+ * is that padded length; pack/unpack convert device-resident vectors (asynchronously on the
+ * plan's stream); the padding slots of a device vector must be zero-initialised. */
+int gsg_plan_dev_size(const gsg_plan* plan, int64_t* size_out);
+int gsg_pack_dev(gsg_plan* plan, const double* ref_layout_dev, double* dev_layout_dev);
+int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_layout_dev);
 /* run all subsequent work of this plan on `stream` (cudaStream_t); NULL = the plan's own */
 int gsg_plan_set_stream(gsg_plan* plan, void* stream);
 int gsg_plan_sync(gsg_plan* plan);
@@ -91,8 +98,8 @@ int gsg_apply_grad(gsg_plan* plan, const double* a, const double* x, double* y);
 /* y = sum_d D_d (D_d x)   `laplacian_matrix(D,k,n) * x`  src/multidim_derivative.jl:71-79 */
 int gsg_apply_laplacian(gsg_plan* plan, const double* x, double* y);
 
-/* ---- operator apply, device vectors --------------------------------------------------------- */
-/* y = alpha * D_d x + beta * y   (beta == 0: y is not read) */
+/* ---- operator apply, device vectors (DEVICE LAYOUT, length gsg_plan_dev_size) ---------------- */
+/* y = alpha * D_d x + beta * y   (beta == 0: y is not read); x and y must not alias */
 int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, double beta,
                     double* y_dev);
 /* y = sum_d a[d] D_d x */

@@ -30,12 +30,11 @@ v1 = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
 t0 = time.time()
 u0 = g.tensor_construct(D, k, n, [v1] * D)
 print(f"tensor_construct {time.time()-t0:.2f}s", flush=True)
-dev = torch.device("cuda:0")
-x = torch.from_numpy(u0).to(dev)
-y = torch.zeros_like(x)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 plan.set_stream(stream)
+x = plan.to_device(u0)
+y = torch.zeros_like(x)
 
 
 def timeit(fn, reps):

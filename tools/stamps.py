@@ -1,0 +1,28 @@
+"""Per-phase clock stamps of the TMA short kernel's CTA 0 (development aid)."""
+import ctypes as C, math, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gsg_b200 as g
+from gsg_b200 import lib
+D, k, n, d = 6, 3, 8, int(sys.argv[1]) if len(sys.argv) > 1 else 1
+beta = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
+plan = g.Plan(D, k, n)
+v1 = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
+x = plan.to_device(g.tensor_construct(D, k, n, [v1] * D))
+y = torch.zeros_like(x)
+lib.gsg_debug_stamps.restype = C.c_int
+lib.gsg_debug_stamps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+for _ in range(2):
+    plan.apply_D_dev(d, x, y, 1.0, beta)
+plan.sync(); torch.cuda.synchronize()
+lib.gsg_debug_stamps(plan._h, None, 0)          # enable
+plan.apply_D_dev(d, x, y, 1.0, beta)
+plan.sync(); torch.cuda.synchronize()
+buf = np.zeros(64 * 8, dtype=np.int64)
+lib.gsg_debug_stamps(plan._h, buf.ctypes.data_as(C.c_void_p), 64 * 8)
+b = buf.reshape(64, 8)
+t0 = b[0, 0]
+print("it | prod: wait_done  store_issue  wait_read  load_issue | comp: wait_full  compute | abs start")
+for it in range(40):
+    c0, c1, c2, c3, c4, w0, w1, w2 = b[it]
+    print(f"{it:2d} | {c1-c0:8d} {c2-c1:8d} {c3-c2:8d} {c4-c3:8d} | {w1-w0:8d} {w2-w1:8d} | {c0-t0:9d} {w0-t0:9d}")

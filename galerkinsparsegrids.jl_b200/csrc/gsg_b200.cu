@@ -94,6 +94,8 @@ struct SweepClass {          // one launch of a sweep
     Kind kind = Kind::GENERIC;
     int NPOLE = 0, Amin = 0; // generic kernel parameters
     int nwarps = 8;          // long kernel: warps per CTA
+    int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
+    DevBuf<int> partBlk, partRow;
     size_t smem = 0;
     DevBuf<TileDev> tiles;
     DevBuf<TileLong> ltiles;
@@ -126,8 +128,9 @@ struct gsg_plan {
     std::vector<double> dense_host;                        // concatenated, passed as kernel parameter
     int hoff[5] = {0, 0, 0, 0, 0};
     int htotal = 0, short_pmax = -1;
-    std::vector<std::unique_ptr<DevBuf<int>>> ptab;        // index p: [wsplit (nw+1) | rowend (2^p)]
-    std::vector<int> ptab_nw;
+    // long kernel: per p, the principal sub-block as a compact stream of block records
+    std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
+    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
 
     std::vector<Direction> dirs;
 
@@ -210,32 +213,43 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
 
-    // long kernel tables per p: block-rows split over the CTA's warps (balanced in block count)
-    // and the end of each row's blocks inside the principal sub-block
-    P.ptab.resize(n + 1);
-    P.ptab_nw.assign(n + 1, 0);
-    for (int p = 0; p <= n; ++p) {
-        const int nq = 1 << p;
-        const int nw = std::min(16, std::max(std::min(4, nq), nq / 4));
-        std::vector<long long> pre(nq + 1, 0);
-        std::vector<int> tab(nw + 1 + nq, 0);
-        for (int q = 0; q < nq; ++q) {
-            int b = rowptr[q];
-            while (b < rowptr[q + 1] && col[b] < nq) ++b;
-            tab[nw + 1 + q] = b;
-            pre[q + 1] = pre[q] + (b - rowptr[q]) + 1;     // +1: per-row epilogue cost
+    // long kernel: per p the principal sub-block (rows and columns < 2^p) as a stream of block
+    // records {K*K values row-major, int col, int flags (bit 0 = last record of its block-row)};
+    // every row owns at least one record so the end-of-row flag always exists
+    P.lrec.resize(n + 1);
+    P.lrow_start.assign(n + 1, {});
+    {
+        const int KK = K * K;
+        const int REC = (KK * 8 + 8 + 15) & ~15;
+        for (int p = 0; p <= n; ++p) {
+            const int nq = 1 << p;
+            std::vector<unsigned char> buf;
+            std::vector<int>& rs = P.lrow_start[p];
+            rs.assign(nq + 1, 0);
+            int nrec = 0;
+            for (int q = 0; q < nq; ++q) {
+                rs[q] = nrec;
+                int cnt = 0;
+                for (int b = rowptr[q]; b < rowptr[q + 1] && col[b] < nq; ++b) ++cnt;
+                const int emit = std::max(cnt, 1);
+                for (int i = 0; i < emit; ++i) {
+                    buf.resize((size_t)(nrec + 1) * REC, 0);
+                    unsigned char* rec = buf.data() + (size_t)nrec * REC;
+                    int meta[2] = {0, i == emit - 1 ? 1 : 0};
+                    if (i < cnt) {
+                        const int b = rowptr[q] + i;
+                        std::memcpy(rec, val.data() + (size_t)b * P.KK2, (size_t)KK * 8);
+                        meta[0] = col[b];
+                    }
+                    std::memcpy(rec + KK * 8, meta, 8);
+                    ++nrec;
+                }
+            }
+            rs[nq] = nrec;
+            buf.resize((size_t)(nrec + 2 * LONG_CH) * REC, 0);     // over-read slack for whole-chunk copies
+            P.lrec[p].reset(new DevBuf<unsigned char>());
+            GSG_TRY(P.lrec[p]->upload(buf));
         }
-        tab[0] = 0;
-        int q = 0;
-        for (int w = 1; w < nw; ++w) {
-            const long long target = pre[nq] * w / nw;
-            while (q < nq && pre[q] < target) ++q;
-            tab[w] = std::max(q, tab[w - 1]);
-        }
-        tab[nw] = nq;
-        P.ptab[p].reset(new DevBuf<int>());
-        GSG_TRY(P.ptab[p]->upload(tab));
-        P.ptab_nw[p] = nw;
     }
 
     // dense principal sub-blocks for the register-resident short classes
@@ -344,7 +358,11 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
-        const size_t long_smem = (size_t)NP * 32 * sizeof(double) + (size_t)P.ptab_nw[p] * K * 32 * sizeof(double);
+        const int REC = (K * K * 8 + 8 + 15) & ~15;
+        const size_t warp_bytes = (size_t)LONG_NBUF * LONG_CH * REC + (size_t)K * 32 * 8;
+        int nw = NQ >= 64 ? 16 : (NQ >= 16 ? 8 : 4);
+        while (nw > 2 && (size_t)NP * 32 * 8 + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw /= 2;
+        const size_t long_smem = (size_t)NP * 32 * 8 + nw * warp_bytes;
         if (short_supported(K, p)) {
             if (tma_active) continue;
             c.kind = Kind::SHORT;
@@ -355,7 +373,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         }
         if (c.kind == Kind::LONG) {
             std::vector<TileLong> ll;
-            c.nwarps = P.ptab_nw[p];
+            c.nwarps = nw;
             c.smem = long_smem;
             const int A = dir.A, B = PI / A;
             for (size_t gi = 0; gi < groups.size(); ++gi) {
@@ -378,9 +396,35 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
                         ll.push_back(TileLong{(int)gi, r0, 0, (short)std::min(nrmax, groups[gi].nitems - r0), (short)A, (short)B, 0});
                 }
             }
-            c.ntiles = (int)ll.size();
-            if (c.ntiles == 0) continue;
-            GSG_TRY(c.ltiles.upload(ll));
+            if (ll.empty()) continue;
+            // row parts: enough CTAs to cover the GPU twice, but at least ~32 records per warp
+            const std::vector<int>& rs = P.lrow_start[p];
+            const int nrec = rs[NQ];
+            int rsplit = (int)std::min<long long>((2LL * P.sm_count + (long long)ll.size() - 1) / (long long)ll.size(),
+                                                  std::max(1, nrec / (nw * 32)));
+            rsplit = std::max(1, std::min(rsplit, 64));
+            c.rsplit = rsplit;
+            const int G = rsplit * nw;
+            std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
+            pb[0] = 0; pr[0] = 0;
+            {
+                const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
+                int q = 0;
+                for (int g = 1; g < G; ++g) {
+                    const long long target = total * g / G;
+                    while (q < NQ && (long long)rs[q] + q < target) ++q;
+                    pr[g] = std::max(q, pr[g - 1]);
+                    pb[g] = rs[pr[g]];
+                }
+            }
+            GSG_TRY(c.partBlk.upload(pb));
+            GSG_TRY(c.partRow.upload(pr));
+            std::vector<TileLong> full;
+            full.reserve(ll.size() * rsplit);
+            for (int part = 0; part < rsplit; ++part)       // coarse (long) rows first
+                for (TileLong tl1 : ll) { tl1.part = (short)part; full.push_back(tl1); }
+            c.ntiles = (int)full.size();
+            GSG_TRY(c.ltiles.upload(full));
             dir.classes.push_back(std::move(c));
             continue;
         }
@@ -516,10 +560,8 @@ int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swe
         auto kern = sweep_long_kernel<K>;
         static thread_local size_t configured = 0;
         GSG_TRY(ensure_smem(kern, c.smem, configured));
-        Bcsr M{pl.b_rowptr.p, pl.b_col.p, pl.b_val.p, pl.KK2};
-        const int* tab = pl.ptab[c.p]->p;
-        kern<<<c.ntiles, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p, M, tab,
-                                                       tab + c.nwarps + 1, c.p, (int)pl.S.kDp, dir.A);
+        kern<<<c.ntiles, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p, pl.lrec[c.p]->p,
+                                                       c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_long", K, c);
     }

@@ -505,13 +505,14 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 
 // ------------------------------------------------------------------------------------------
 // Long poles (p >= 4 at k = 3): lanes = poles.  A tile holds PT <= 32 poles (a sub-range
-// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles); the
-// whole x tile sits in shared memory as xs[row][32] (conflict-free for lanes = poles).  The
-// block-rows of the K x K block-CSR matrix are split over the CTA's warps by a host-computed
-// partition balanced in block count; for each block the warp loads the K x K values with
-// uniform (broadcast) 128-bit loads, K x values per lane from shared memory and issues K*K
-// DFMAs.  Each finished block-row (K*PT values) goes through a per-warp scratch so that the
-// global write is coalesced in memory order.
+// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles) and
+// one ROW PART of the principal sub-block; the whole x tile sits in shared memory as xs[row][32]
+// (conflict-free for lanes = poles).  The matrix of class p is a compact stream of K x K block
+// records (values, block column, end-of-row flag) in row order.  Every warp owns a contiguous
+// range of whole block-rows (host partition balanced in block count) and streams its records
+// through a private 3-deep cp.async ring in shared memory, so no L2 latency is exposed in the
+// inner loop: per record 5 broadcast LDS.128 + K conflict-free LDS.64 of x + K*K DFMAs.  Each
+// finished block-row goes through a per-warp scratch so the global write is coalesced.
 //   in-item order t -> a = t % na, m = (t / na) % K, bl = t / (K*na):
 //   pole = a + na*bl, in-cell offset = ebase + a + A*m + K*A*bl.
 // ------------------------------------------------------------------------------------------
@@ -519,17 +520,39 @@ struct TileLong {
     int group;
     int r0;
     int ebase;
-    short nr, na, nb, pad;
+    short nr, na, nb, part;   // part: which row part of the matrix this CTA computes
 };
+
+constexpr int LONG_CH = 8;      // records per ring chunk
+constexpr int LONG_NBUF = 3;    // ring depth
+
+template <int K>
+struct LongRec {
+    static constexpr int KK = K * K;
+    static constexpr int BYTES = (KK * 8 + 8 + 15) & ~15;     // values + {col, flags}, 16-byte multiple
+};
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int K>
 __global__ void __launch_bounds__(512)
 sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
-                  const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles, Bcsr M,
-                  const int* __restrict__ wsplit, const int* __restrict__ rowend, int p, int KDp, int A) {
-    constexpr int KK2 = (K * K + 1) & ~1;
+                  const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles,
+                  const unsigned char* __restrict__ recs, const int* __restrict__ partBlk,
+                  const int* __restrict__ partRow, int p, int KDp, int A) {
+    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
+    constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
+    constexpr int WARP_BYTES = LONG_NBUF * CHB + K * 32 * 8;  // ring + scratch per warp
     const int NQ = 1 << p, NP = K * NQ;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ long long sbase[MAXL + 1];
     __shared__ int sS;
     __shared__ short tab_row[K * 32];   // m*32 + pole-in-item
@@ -542,8 +565,25 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     const int PIt = na * nb;            // poles per item in this tile
     const int PT = nr * PIt;            // poles in the tile (<= 32)
     const int TL = K * PIt;
-    double* xs = smem;                                   // NP * 32
-    double* scratch = smem + (size_t)NP * 32 + (size_t)warp * (K * 32);
+    double* xs = reinterpret_cast<double*>(smraw);                                  // NP * 32
+    unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + (size_t)warp * WARP_BYTES;
+    unsigned char* ring = wbase;
+    double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * CHB);
+
+    // this warp's records [b0, b1) and first block-row q
+    const int gpart = t.part * nwarp + warp;
+    const int b0 = partBlk[gpart], b1 = partBlk[gpart + 1];
+    int q = partRow[gpart];
+    const int c_first = b0 / LONG_CH, c_last = b1 > b0 ? (b1 - 1) / LONG_CH : c_first - 1;
+
+    auto issue_chunk = [&](int c) {
+        if (c <= c_last) {
+            const unsigned char* src = recs + (size_t)c * CHB;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (c % LONG_NBUF) * CHB);
+            for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
+        }
+        cp_async_commit();
+    };
 
     if (tid <= p) sbase[tid] = groups[t.group].base[tid];
     if (tid == 32) sS = groups[t.group].S;
@@ -553,66 +593,73 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
         tab_row[tt] = (short)(m * 32 + a + na * bl);
         tab_g[tt] = t.ebase + a + A * m + K * A * bl;
     }
+    issue_chunk(c_first);
+    issue_chunk(c_first + 1);
     __syncthreads();
     const int S = sS;
 
-    // ---- stage in
+    // ---- stage the x tile in (asynchronous 8-byte copies, transposed to xs[row][pole])
     const int ncell = NQ * nr;
     for (int c = warp; c < ncell; c += nwarp) {
-        const int q = c / nr, r = c - q * nr;
-        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KDp);
-        double* dst = xs + (size_t)q * K * 32 + r * PIt;
-        for (int tt = lane; tt < TL; tt += 32) dst[tab_row[tt]] = src[tab_g[tt]];
+        const int qq = c / nr, r = c - qq * nr;
+        const double* src = X + cell_addr(sbase, S, qq, t.r0 + r, KDp);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + (size_t)qq * K * 32 + r * PIt);
+        for (int tt = lane; tt < TL; tt += 32) cp_async8(dst + tab_row[tt] * 8, src + tab_g[tt]);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
-    // ---- block-rows of this warp
-    const int q1 = wsplit[warp + 1];
+    // ---- stream this warp's block records
     const bool active = lane < PT;
-    for (int q = wsplit[warp]; q < q1; ++q) {
-        double acc[K];
+    double acc[K];
 #pragma unroll
-        for (int m = 0; m < K; ++m) acc[m] = 0.0;
-        const int b1 = rowend[q];        // blocks with column < NQ (principal sub-block), counted loop
-#pragma unroll 2
-        for (int blk = M.rowptr[q]; blk < b1; ++blk) {
-            const int qc = __ldg(M.col + blk);
-            const double2* hv = reinterpret_cast<const double2*>(M.val + (size_t)blk * KK2);
-            double h[KK2];
-#pragma unroll
-            for (int i = 0; i < KK2 / 2; ++i) {
-                const double2 v = __ldg(hv + i);
-                h[2 * i] = v.x;
-                h[2 * i + 1] = v.y;
-            }
-            const double* xv = xs + (size_t)qc * K * 32 + lane;
+    for (int m = 0; m < K; ++m) acc[m] = 0.0;
+    for (int c = c_first; c <= c_last; ++c) {
+        issue_chunk(c + 2);
+        cp_async_wait<2>();            // chunk c has landed (this thread's copies) ...
+        __syncwarp();                  // ... and every lane's
+        const unsigned char* buf = ring + (c % LONG_NBUF) * CHB;
+        const int lo = max(b0, c * LONG_CH) - c * LONG_CH, hi = min(b1, (c + 1) * LONG_CH) - c * LONG_CH;
+        for (int i = lo; i < hi; ++i) {
+            const unsigned char* rec = buf + i * REC;
+            const int2 meta = *reinterpret_cast<const int2*>(rec + KK * 8);
+            const double* hv = reinterpret_cast<const double*>(rec);
+            const double* xv = xs + (size_t)meta.x * K * 32 + lane;
             double xr[K];
 #pragma unroll
             for (int mi = 0; mi < K; ++mi) xr[mi] = xv[mi * 32];
 #pragma unroll
             for (int mo = 0; mo < K; ++mo)
 #pragma unroll
-                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(h[mo * K + mi], xr[mi], acc[mo]);
-        }
-        __syncwarp();
-        if (active) {
+                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(hv[mo * K + mi], xr[mi], acc[mo]);
+            if (meta.y & 1) {          // end of block-row q: coalesced write through the scratch
+                __syncwarp();
+                if (active) {
 #pragma unroll
-            for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
-        }
-        __syncwarp();
-        for (int r = 0; r < nr; ++r) {
-            double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
-            const double* sc = scratch + r * PIt;
-            if (beta == 0.0) {
-                for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
-            } else {
-                for (int tt = lane; tt < TL; tt += 32) {
-                    const int g = tab_g[tt];
-                    dstg[g] = fma(alpha, sc[tab_row[tt]], beta * dstg[g]);
+                    for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
                 }
+                __syncwarp();
+                for (int r = 0; r < nr; ++r) {
+                    double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
+                    const double* sc = scratch + r * PIt;
+                    if (beta == 0.0) {
+                        for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
+                    } else {
+                        for (int tt = lane; tt < TL; tt += 32) {
+                            const int g = tab_g[tt];
+                            dstg[g] = fma(alpha, sc[tab_row[tt]], beta * dstg[g]);
+                        }
+                    }
+                }
+                ++q;
+#pragma unroll
+                for (int m = 0; m < K; ++m) acc[m] = 0.0;
             }
         }
+        __syncwarp();                  // chunk buffer may be refilled two iterations later
     }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -318,6 +318,25 @@ class Plan:
     def sync(self) -> None:
         check(lib.gsg_plan_sync(self._h))
 
+    def set_shard(self, rank: int, nranks: int) -> None:
+        check(lib.gsg_plan_set_shard(self._h, rank, nranks))
+
+    def rk_stage_dev(self, length: int, u, k, acc, w, cw: float, ca: float, first: bool) -> None:
+        check(lib.gsg_rk_stage_dev(self._h, int(length), _devptr(u), _devptr(k), _devptr(acc), _devptr(w),
+                                   float(cw), float(ca), 1 if first else 0))
+
+    def rk_final_dev(self, length: int, u, k, acc, ca: float) -> None:
+        check(lib.gsg_rk_final_dev(self._h, int(length), _devptr(u), _devptr(k), _devptr(acc), float(ca)))
+
+    def profile_enable(self, on: bool = True) -> None:
+        check(lib.gsg_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """(launches, total_ms, dofs) of the timed streaming-kernel launches."""
+        n, ms, dofs = C.c_int64(), C.c_double(), C.c_double()
+        check(lib.gsg_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(dofs)))
+        return n.value, ms.value, dofs.value
+
     def pack_dev(self, ref_vec, dev_vec) -> None:
         """reference-layout device vector (length size) -> device layout (length dev_size)."""
         check(lib.gsg_pack_dev(self._h, _devptr(ref_vec), _devptr(dev_vec)))

@@ -102,6 +102,7 @@ struct SweepClass {          // one launch of a sweep
     DevBuf<TileS> stiles;
     ShortParams sprm{};
     int ntiles = 0;
+    double short_dofs = 0;   // SHORT_TMA: DOFs this launch processes (for the roofline figure)
 };
 
 struct Direction {
@@ -149,6 +150,15 @@ struct gsg_plan {
     DevBuf<double> wpts, wout;
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
+
+    // multi-GPU work sharing: this process launches tiles [rank*nt/nranks, (rank+1)*nt/nranks)
+    int shard_rank = 0, shard_n = 1;
+
+    // optional timing of the dominant (streaming) kernel with CUDA events on its stream
+    bool prof_on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    size_t prof_used = 0;
+    double prof_dofs = 0;         // DOFs processed by the profiled launches
 };
 
 struct gsg_csr {
@@ -340,6 +350,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
                 }
             }
             c.ntiles = (int)tl.size();
+            for (const TileS& t : tl) c.short_dofs += (double)(1 << t.P) * t.nr * KD;
             if (c.ntiles > 0) {
                 GSG_TRY(c.stiles.upload(tl));
                 c.sprm.KD = KD;
@@ -485,6 +496,13 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     return 0;
 }
 
+// tile range of this process (multi-GPU work sharing)
+inline void tile_range(const gsg_plan& pl, int ntiles, int& begin, int& count) {
+    begin = (int)((long long)ntiles * pl.shard_rank / pl.shard_n);
+    const int end = (int)((long long)ntiles * (pl.shard_rank + 1) / pl.shard_n);
+    count = end - begin;
+}
+
 int launch_check(const char* what, int K, const SweepClass& c) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && getenv("GSG_DEBUG_SYNC")) e = cudaDeviceSynchronize();
@@ -513,14 +531,24 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         auto kern = sweep_short_tma_kernel<K>;
         static thread_local size_t configured = 0;
         GSG_TRY(ensure_smem(kern, c.smem, configured));
-        const int grid = std::min(c.ntiles, pl.sm_count);
+        int tb, tn;
+        tile_range(pl, c.ntiles, tb, tn);
+        if (tn == 0) return 0;
+        const int grid = std::min(tn, pl.sm_count);
         static_assert(sizeof(HDense<K>) + 256 < 32000, "dense blocks must fit the kernel parameter space");
         HDense<K> hd;
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
         std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
+        const bool prof = pl.prof_on && pl.prof_used < pl.prof_ev.size();
+        if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
-                                                                         c.stiles.p, c.ntiles, hd, c.sprm, pl.dbg);
+                                                                         c.stiles.p + tb, tn, hd, c.sprm, pl.dbg);
+        if (prof) {
+            GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, st));
+            ++pl.prof_used;
+            pl.prof_dofs += c.short_dofs * (double)tn / (double)c.ntiles;
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_short_tma", K, c);
     }
@@ -533,8 +561,11 @@ int launch_short_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const S
     auto kern = sweep_short_kernel<K, P>;
     static thread_local size_t configured = 0;
     GSG_TRY(ensure_smem(kern, c.smem, configured));
-    kern<<<c.ntiles, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, pl.dense[P]->p, (int)pl.S.kD,
-                                         (int)pl.S.kDp, dir.A);
+    int tb, tn;
+    tile_range(pl, c.ntiles, tb, tn);
+    if (tn == 0) return 0;
+    kern<<<tn, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p + tb, pl.dense[P]->p, (int)pl.S.kD,
+                                   (int)pl.S.kDp, dir.A);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_check("sweep_short", K, c);
 }
@@ -560,8 +591,11 @@ int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swe
         auto kern = sweep_long_kernel<K>;
         static thread_local size_t configured = 0;
         GSG_TRY(ensure_smem(kern, c.smem, configured));
-        kern<<<c.ntiles, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p, pl.lrec[c.p]->p,
-                                                       c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
+        int tb, tn;
+        tile_range(pl, c.ntiles, tb, tn);
+        if (tn == 0) return 0;
+        kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
+                                                 c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_long", K, c);
     }
@@ -575,8 +609,11 @@ int launch_generic_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
     static thread_local size_t configured = 0;
     GSG_TRY(ensure_smem(kern, c.smem, configured));
     Bcsr M{pl.b_rowptr.p, pl.b_col.p, pl.b_val.p, pl.KK2};
-    kern<<<c.ntiles, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p, M, pl.S.k, c.p, (int)pl.S.kDp,
-                                         dir.A, c.NPOLE, c.Amin);
+    int tb, tn;
+    tile_range(pl, c.ntiles, tb, tn);
+    if (tn == 0) return 0;
+    kern<<<tn, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p + tb, M, pl.S.k, c.p, (int)pl.S.kDp,
+                                   dir.A, c.NPOLE, c.Amin);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_check("sweep_generic", K, c);
 }
@@ -867,6 +904,7 @@ int gsg_plan_destroy(gsg_plan* plan) {
     for (cudaEvent_t ev : plan->ev_done) if (ev) cudaEventDestroy(ev);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
+    for (auto& pr : plan->prof_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     delete plan;
     return 0;
 }
@@ -905,6 +943,64 @@ int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_lay
     GSG_TRY(check_plan(plan));
     if (!ref_layout_dev || !dev_layout_dev) return fail(GSG_ERR_ARG, "null pointer");
     return copy_out(*plan, ref_layout_dev, dev_layout_dev, cudaMemcpyDeviceToDevice);
+}
+
+int gsg_plan_set_shard(gsg_plan* plan, int rank, int nranks) {
+    if (!plan || nranks < 1 || rank < 0 || rank >= nranks) return fail(GSG_ERR_ARG, "bad shard");
+    plan->shard_rank = rank;
+    plan->shard_n = nranks;
+    return 0;
+}
+
+int gsg_rk_stage_dev(gsg_plan* plan, int64_t len, const double* u, const double* k, double* acc, double* w,
+                     double cw, double ca, int first) {
+    GSG_TRY(check_plan(plan));
+    if (len < 0 || !u || !k || !acc || !w) return fail(GSG_ERR_ARG, "bad argument");
+    if (len == 0) return 0;
+    rk_stage_kernel<<<elementwise_grid(*plan, len), 256, 0, plan->stream>>>(len, u, k, acc, w, cw, ca, first);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GSG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gsg_rk_final_dev(gsg_plan* plan, int64_t len, double* u, const double* k, const double* acc, double ca) {
+    GSG_TRY(check_plan(plan));
+    if (len < 0 || !u || !k || !acc) return fail(GSG_ERR_ARG, "bad argument");
+    if (len == 0) return 0;
+    rk_final_kernel<<<elementwise_grid(*plan, len), 256, 0, plan->stream>>>(len, u, k, acc, ca);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GSG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gsg_profile_enable(gsg_plan* plan, int on) {
+    GSG_TRY(check_plan(plan));
+    if (on && plan->prof_ev.empty()) {
+        plan->prof_ev.resize(4096);
+        for (auto& pr : plan->prof_ev) {
+            GSG_CUDA(cudaEventCreate(&pr.first));
+            GSG_CUDA(cudaEventCreate(&pr.second));
+        }
+    }
+    plan->prof_on = on != 0;
+    plan->prof_used = 0;
+    plan->prof_dofs = 0;
+    return 0;
+}
+
+int gsg_profile_read(gsg_plan* plan, int64_t* launches_out, double* total_ms_out, double* dofs_out) {
+    GSG_TRY(check_plan(plan));
+    GSG_CUDA(cudaDeviceSynchronize());
+    double total = 0;
+    for (size_t i = 0; i < plan->prof_used; ++i) {
+        float ms = 0;
+        GSG_CUDA(cudaEventElapsedTime(&ms, plan->prof_ev[i].first, plan->prof_ev[i].second));
+        total += ms;
+    }
+    if (launches_out) *launches_out = (int64_t)plan->prof_used;
+    if (total_ms_out) *total_ms_out = total;
+    if (dofs_out) *dofs_out = plan->prof_dofs;
+    return 0;
 }
 
 // development aid: enable (n > 0) / read back the per-phase clock stamps of the TMA kernel's CTA 0

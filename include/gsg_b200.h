@@ -117,6 +117,23 @@ int gsg_rk4_wave_dev(gsg_plan* plan, double* u_dev, double* v_dev, double dt, in
 /* E = sum_d |D_d u|^2 + |udot|^2     energy_func, src/pdes.jl:258-273 */
 int gsg_energy(gsg_plan* plan, const double* u, const double* udot, double* energy_out);
 
+/* ---- building blocks for host-driven / multi-GPU time stepping (device layout) ------------ */
+/* Multi-GPU work sharing: after set_shard(rank, nranks) every sweep of this plan launches only
+ * this rank's contiguous slice of each tile list, i.e. it ACCUMULATES a partial operator result
+ * (the slices of all ranks sum to the full result; use beta = 1 into a zeroed vector). */
+int gsg_plan_set_shard(gsg_plan* plan, int rank, int nranks);
+/* w = u + cw*k ; acc = (first ? u : acc) + ca*k   on `len` entries (any sub-range) */
+int gsg_rk_stage_dev(gsg_plan* plan, int64_t len, const double* u, const double* k, double* acc,
+                     double* w, double cw, double ca, int first);
+/* u = acc + ca*k */
+int gsg_rk_final_dev(gsg_plan* plan, int64_t len, double* u, const double* k, const double* acc,
+                     double ca);
+/* Time the dominant (streaming TMA) sweep kernel with CUDA events on the stream it is launched
+ * on; read returns the number of timed launches, their summed duration and the DOFs they
+ * processed (bench.py's roofline figure). */
+int gsg_profile_enable(gsg_plan* plan, int on);
+int gsg_profile_read(gsg_plan* plan, int64_t* launches_out, double* total_ms_out, double* dofs_out);
+
 /* ---- batched reconstruct_DG -------------------------------------------------------------------- */
 /* out[i] = reconstruct_DG(V2D(vcoeffs), points[:, i])   src/dg_methods.jl:150-165;
  * points is a column-major D x npts matrix (Julia Matrix{Float64}).  Called once per point

@@ -1,0 +1,185 @@
+"""ctypes front-end of oracle/csc_kernels.c -- TEST / BASELINE INFRASTRUCTURE ONLY.
+
+Provides (a) the reference-style assembled matrix D_d (literal column loop of
+src/multidim_derivative.jl:32-55 restated in C) for mid-size cross-checks, and (b) the CPU
+baseline of the hot path: Julia's serial CSC column-scatter `A*x` (src/pdes.jl:63,179-180) and an
+OpenMP CSR analogue of the optional MKLSparse path (src/GalerkinSparseGrids.jl:5-7), timed on a
+BOUNDED, strided sample of columns / rows of the real operator and extrapolated by nnz.
+Imported only by tests/, bench.py's cpu_baseline / --impl reference legs and smoke()."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "csc_kernels.c")
+_LIB = os.path.join(_HERE, "libgsg_oracle_c.so")
+
+
+def _build():
+    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
+        subprocess.run(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+                        _SRC, "-o", _LIB], check=True)
+
+
+def _load():
+    _build()
+    lib = C.CDLL(_LIB)
+    i64, f64, vp = C.c_int64, C.c_double, C.c_void_p
+    lib.gsgo_get_size.restype = i64
+    lib.gsgo_get_size.argtypes = [C.c_int] * 4
+    lib.gsgo_assemble_cols.restype = i64
+    lib.gsgo_assemble_cols.argtypes = [C.c_int] * 5 + [vp, vp, vp, i64, i64, vp, vp, vp, i64]
+    lib.gsgo_spmv_csc.restype = None
+    lib.gsgo_spmv_csc.argtypes = [i64, vp, vp, vp, vp, vp]
+    lib.gsgo_spmv_csr_omp.restype = None
+    lib.gsgo_spmv_csr_omp.argtypes = [i64, vp, vp, vp, vp, vp]
+    lib.gsgo_axpy.restype = None
+    lib.gsgo_axpy.argtypes = [i64, f64, vp, vp]
+    lib.gsgo_max_threads.restype = C.c_int
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_SCHEME = {"sparse": 0, "full": 1}
+
+
+def _H_arrays(H):
+    """H: gsg_oracle.CSC or scipy csc -> 0-based int64 colptr/rowval + values."""
+    if hasattr(H, "colptr"):
+        return (np.ascontiguousarray(H.colptr, dtype=np.int64), np.ascontiguousarray(H.rowval, dtype=np.int64),
+                np.ascontiguousarray(H.nzval, dtype=np.float64))
+    import scipy.sparse as sp
+    H = sp.csc_matrix(H)
+    H.sort_indices()
+    return (H.indptr.astype(np.int64), H.indices.astype(np.int64), np.ascontiguousarray(H.data, dtype=np.float64))
+
+
+def get_size(D, k, n, scheme="sparse"):
+    return int(lib().gsgo_get_size(D, k, n, _SCHEME[scheme]))
+
+
+def assemble_cols(D, d, k, n, H, col_begin, col_end, scheme="sparse"):
+    """Columns [col_begin, col_end) of D_d as (colptr, rowval, nzval), 0-based int64."""
+    hc, hr, hv = _H_arrays(H)
+    ncols = col_end - col_begin
+    colptr = np.empty(ncols + 1, dtype=np.int64)
+    nnz = lib().gsgo_assemble_cols(D, k, n, _SCHEME[scheme], d, _p(hc), _p(hr), _p(hv), col_begin, col_end,
+                                   _p(colptr), None, None, 0)
+    if nnz < 0:
+        raise RuntimeError("gsgo_assemble_cols failed")
+    rowval = np.empty(nnz, dtype=np.int64)
+    nzval = np.empty(nnz, dtype=np.float64)
+    lib().gsgo_assemble_cols(D, k, n, _SCHEME[scheme], d, _p(hc), _p(hr), _p(hv), col_begin, col_end,
+                             _p(colptr), _p(rowval), _p(nzval), nnz)
+    return colptr, rowval, nzval
+
+
+def D_matrix(D, d, k, n, H, scheme="sparse"):
+    """Full assembled D_d as scipy CSC (what `D_matrix(D, d, k, n)` returns in the reference)."""
+    import scipy.sparse as sp
+    N = get_size(D, k, n, scheme)
+    colptr, rowval, nzval = assemble_cols(D, d, k, n, H, 0, N, scheme)
+    return sp.csc_matrix((nzval, rowval, colptr), shape=(N, N))
+
+
+def spmv_csc(colptr, rowval, nzval, x, y):
+    lib().gsgo_spmv_csc(colptr.size - 1, _p(colptr), _p(rowval), _p(nzval), _p(x), _p(y))
+
+
+def total_nnz(D, k, n, H, scheme="sparse"):
+    """nnz of one assembled D_d: sum over pole groups of poles * nnz(H[:N', :N'])."""
+    import gsg_oracle as o
+    hc, hr, hv = _H_arrays(H)
+    N1 = hc.size - 1
+    # nnz of each principal sub-block
+    cols = np.repeat(np.arange(N1), np.diff(hc))
+    nnz_p = {}
+    for p in range(n + 1):
+        Np = k << p
+        nnz_p[p] = int(np.count_nonzero((cols < Np) & (hr < Np)))
+    blocks, _ = o.block_table(D - 1, k, n, scheme) if D > 1 else ([((), 0, ())], 0)
+    total = 0
+    for lv, _off, ks in blocks:
+        p = n if scheme == "full" else n - sum(lv)
+        npoles = k ** (D - 1) * int(np.prod(ks, dtype=np.int64)) if D > 1 else 1
+        total += npoles * nnz_p[p]
+    return total
+
+
+def rk4_cpu_baseline(D, k, n, H, budget_s=15.0, threads=1, chunk=4096, scheme="sparse", seed=0):
+    """Estimate RK4 DOF-updates/s of the reference's CPU path at (D, k, n).
+
+    threads == 1: Julia's serial CSC column scatter (stock SparseArrays).
+    threads  > 1: OpenMP row-parallel CSR (MKLSparse analogue), all host threads.
+    For every direction d a strided sample of `chunk`-wide column (row) slabs of the REAL
+    operator is assembled and multiplied against full-length vectors; the measured time is
+    scaled by nnz_total / nnz_sampled.  One RK4 step = 4 RHS x D products + vector updates."""
+    N = get_size(D, k, n, scheme)
+    nnz_total = total_nnz(D, k, n, H, scheme)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(N)
+    y = np.zeros(N)
+    # a few large CONTIGUOUS slabs per direction (realistic cache reuse inside a slab), sized
+    # from a rough assembly+product rate so that the whole measurement fits the budget
+    nslab = 8
+    cols_budget = budget_s * 1.0e6 / D                    # ~1e6 columns/s assembled and multiplied
+    slab = int(max(chunk, min(N // nslab, cols_budget // nslab)))
+    if threads > 1:
+        import scipy.sparse as sp
+        hc, hr, hv = _H_arrays(H)
+        Ht = sp.csc_matrix((hv, hr, hc), shape=(k << n, k << n)).T.tocsc()
+        Ht.sort_indices()
+    t_products = 0.0
+    sampled = 0
+    per_dir = []
+    for d in range(1, D + 1):
+        t_d, nnz_d = 0.0, 0
+        for si in range(nslab):
+            b = int((N - slab) * (si + 0.5 * ((d - 1) / D)) / nslab)      # de-phase the directions
+            e = min(N, b + slab)
+            if threads == 1:
+                colptr, rowval, nzval = assemble_cols(D, d, k, n, H, b, e, scheme)
+                xs = np.ascontiguousarray(x[b:e])
+                t0 = time.perf_counter()
+                spmv_csc(colptr, rowval, nzval, xs, y)
+                t_d += time.perf_counter() - t0
+            else:
+                rowptr, colidx, nzval = assemble_cols(D, d, k, n, Ht, b, e, scheme)   # rows of D_d
+                ys = np.empty(e - b)
+                t0 = time.perf_counter()
+                lib().gsgo_spmv_csr_omp(e - b, _p(rowptr), _p(colidx), _p(nzval), _p(x), _p(ys))
+                t_d += time.perf_counter() - t0
+            nnz_d += nzval.size
+        per_dir.append(t_d * nnz_total / max(nnz_d, 1))
+        t_products += t_d
+        sampled += nnz_d
+    # vector arithmetic of one RK4 step: sum of D product vectors per RHS + stage updates
+    t0 = time.perf_counter()
+    lib().gsgo_axpy(N, 0.5, _p(x), _p(y))
+    t_axpy = time.perf_counter() - t0
+    n_axpy = 4 * D + 10
+    t_step = 4.0 * sum(per_dir) + n_axpy * t_axpy
+    return {
+        "N": N, "nnz_per_direction": nnz_total, "nnz_sampled": sampled, "sample_fraction": sampled / (D * nnz_total),
+        "t_products_measured_s": t_products, "t_spmv_full_est_s": per_dir, "t_axpy_s": t_axpy,
+        "t_step_est_s": t_step, "dof_updates_per_s": N / t_step, "threads": threads,
+        "nnz_per_s": sampled / max(t_products, 1e-12),
+    }

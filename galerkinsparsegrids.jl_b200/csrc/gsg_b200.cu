@@ -148,6 +148,7 @@ struct gsg_plan {
     // workspaces (device layout)
     DevBuf<double> wx, wy, wk, wacc, ww, wtmp, wred;
     DevBuf<double> wpts, wout;
+    DevBuf<int> tile_counter;     // dynamic tile scheduler of the persistent TMA kernel
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
 
@@ -327,7 +328,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         c.p = P.short_pmax;
         const int cmin = 1 << P.short_pmax;
         int CT = std::max(cmin, (TMA_STAGE_TARGET_DOUBLES / KDp) / cmin * cmin);   // multi-cells per tile
-        const size_t fixed = 128 + (size_t)PI * 4 + 128;
+        const size_t fixed = 128 + 8 * sizeof(TileS) + (size_t)PI * 4 + 128;
         int ns = 4;
         while (ns > 2 && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) --ns;
         while (CT > cmin && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) CT -= cmin;
@@ -372,8 +373,10 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         const int REC = (K * K * 8 + 8 + 15) & ~15;
         const size_t warp_bytes = (size_t)LONG_NBUF * LONG_CH * REC + (size_t)K * 32 * 8;
         int nw = NQ >= 64 ? 16 : (NQ >= 16 ? 8 : 4);
-        while (nw > 2 && (size_t)NP * 32 * 8 + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw /= 2;
-        const size_t long_smem = (size_t)NP * 32 * 8 + nw * warp_bytes;
+        const int nr_long = PI >= 32 ? 1 : 32 / PI;
+        const size_t tile_bytes = (size_t)NP * 32 * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
+        while (nw > 2 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw -= (nw > 8 ? 4 : nw / 2);
+        const size_t long_smem = tile_bytes + nw * warp_bytes;
         if (short_supported(K, p)) {
             if (tma_active) continue;
             c.kind = Kind::SHORT;
@@ -411,8 +414,11 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             // row parts: enough CTAs to cover the GPU twice, but at least ~32 records per warp
             const std::vector<int>& rs = P.lrow_start[p];
             const int nrec = rs[NQ];
-            int rsplit = (int)std::min<long long>((2LL * P.sm_count + (long long)ll.size() - 1) / (long long)ll.size(),
-                                                  std::max(1, nrec / (nw * 32)));
+            // row parts: one CTA per pole set is enough (its warps stream ~nrec/nw records each from
+            // the cp.async ring); only split when a class would otherwise occupy fewer than 16 SMs
+            int rsplit = 1;
+            if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
+            else if ((long long)ll.size() < 16) rsplit = (int)std::min<long long>(16 / (long long)ll.size(), std::max(1, nrec / (nw * 64)));
             rsplit = std::max(1, std::min(rsplit, 64));
             c.rsplit = rsplit;
             const int G = rsplit * nw;
@@ -540,10 +546,12 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
         std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
+        GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < pl.prof_ev.size();
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
-                                                                         c.stiles.p + tb, tn, hd, c.sprm, pl.dbg);
+                                                                         c.stiles.p + tb, tn, hd, c.sprm,
+                                                                         pl.tile_counter.p, pl.dbg);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, st));
             ++pl.prof_used;
@@ -664,11 +672,13 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     }
     // forked launches first: the long-pole CTAs should be resident before the persistent
     // streaming kernel occupies every SM
+    static const int only = getenv("GSG_ONLY_CLASS") ? atoi(getenv("GSG_ONLY_CLASS")) : -1;   // timing aid
     for (size_t i = 1; i < nc; ++i) {
+        if (only >= 0 && (int)i != only) continue;
         cudaStream_t st = fork ? pl.aux[i] : pl.stream;
         GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
     }
-    if (nc > 0) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    if (nc > 0 && (only < 0 || only == 0)) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
     if (fork) {
         for (size_t i = 1; i < nc; ++i) {
             GSG_CUDA(cudaEventRecord(pl.ev_done[i], pl.aux[i]));
@@ -873,6 +883,7 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
         GSG_CUDA(cudaStreamCreateWithFlags(&P->aux[i], cudaStreamNonBlocking));
         GSG_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
     }
+    GSG_TRY(P->tile_counter.resize(4));
     GSG_TRY(build_matrix(*P, H_n, H_colptr, H_rowval, H_nzval));
     P->dirs.resize(D);
     for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d));

@@ -317,12 +317,14 @@ __global__ void __launch_bounds__(32 * (SHORT_TMA_COMPUTE_WARPS + 1), 1)
 sweep_short_tma_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                        const GroupDev* __restrict__ groups, const TileS* __restrict__ tiles, int ntiles,
                        const __grid_constant__ HDense<K> hd, const ShortParams prm,
+                       int* __restrict__ counter,       // dynamic tile scheduler (zeroed before the launch)
                        long long* __restrict__ dbg) {   // dbg: optional per-phase clock stamps (CTA 0)
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);     // full[NS], done[NS]
+    TileS* sdesc = reinterpret_cast<TileS*>(smraw + 128);                        // per-stage tile descriptor
     const int PI = prm.KD / K;
-    int* pole_off = reinterpret_cast<int*>(smraw + 128);
-    size_t off = 128 + (size_t)PI * 4;
+    int* pole_off = reinterpret_cast<int*>(smraw + 128 + 8 * sizeof(TileS));
+    size_t off = 128 + 8 * sizeof(TileS) + (size_t)PI * 4;
     off = (off + 127) & ~(size_t)127;
     double* ring = reinterpret_cast<double*>(smraw + off);
 
@@ -330,7 +332,6 @@ sweep_short_tma_kernel(const double* __restrict__ X, double* __restrict__ Y, dou
     const int warp = tid >> 5, lane = tid & 31;
     const int NS = prm.nstage;
     const int KDp = prm.KDp;
-    const int count = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     for (int j = tid; j < PI; j += blockDim.x) {
         const int b = j / prm.A, a = j - b * prm.A;
@@ -347,54 +348,75 @@ sweep_short_tma_kernel(const double* __restrict__ X, double* __restrict__ Y, dou
 
     if (warp == 0) {
         // ================= TMA producer / storer (warp 0, lanes = 1-D cells) =================
-        const int pre = min(NS, count);
-        for (int it = 0; it < pre; ++it) {
-            const TileS t = tiles[blockIdx.x + (long long)it * gridDim.x];
-            short_tma_load(X, t, ring + (size_t)(it % NS) * prm.stage_doubles, tma::smem_u32(&bars[it % NS]), KDp, lane);
+        // Tiles are claimed with an atomic counter (the CTAs of this persistent kernel may start at
+        // different times because long-pole CTAs of the same sweep share the SMs).  A claimed tile's
+        // descriptor is parked in shared memory for the compute warps; P = -1 marks the end.
+        auto claim_and_load = [&](int s) -> bool {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(counter, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            const unsigned bar = tma::smem_u32(&bars[s]);
+            if (idx >= ntiles) {
+                if (lane == 0) {
+                    sdesc[s].P = -1;
+                    tma::mbar_arrive(bar);          // release the compute warps without data
+                }
+                __syncwarp();
+                return false;
+            }
+            const TileS t = tiles[idx];
+            if (lane == 0) sdesc[s] = t;
+            __syncwarp();
+            short_tma_load(X, t, ring + (size_t)s * prm.stage_doubles, bar, KDp, lane);
+            return true;
+        };
+        int inflight = 0;
+        bool more = true;
+        for (int s = 0; s < NS && more; ++s) {
+            more = claim_and_load(s);
+            if (more) ++inflight;
         }
-        TileS tcur = count > 0 ? tiles[blockIdx.x] : TileS{};
-        for (int it = 0; it < count; ++it) {
+        for (int it = 0; inflight > 0; ++it) {
             const int s = it % NS;
             const unsigned ph = (unsigned)((it / NS) & 1);
-            // prefetch the descriptors needed next while waiting for the compute warps
-            TileS tnext = tcur, tload = tcur;
-            if (it + 1 < count) tnext = tiles[blockIdx.x + (long long)(it + 1) * gridDim.x];
-            if (it + NS < count) tload = tiles[blockIdx.x + (long long)(it + NS) * gridDim.x];
             const long long c0 = clock64();
             tma::mbar_wait(tma::smem_u32(&bars[NS + s]), ph);          // tile computed
             const long long c1 = clock64();
+            const TileS tcur = sdesc[s];
             short_tma_store(Y, tcur, ring + (size_t)s * prm.stage_doubles, KDp, lane, accumulate);
+            --inflight;
             const long long c2 = clock64();
             long long c3 = c2;
-            if (it + NS < count) {
+            if (more) {
                 tma::bulk_wait_read0();        // the stage may be overwritten once its stores have read it
                 __syncwarp();
                 c3 = clock64();
-                short_tma_load(X, tload, ring + (size_t)s * prm.stage_doubles, tma::smem_u32(&bars[s]), KDp, lane);
+                more = claim_and_load(s);
+                if (more) ++inflight;
             }
             if (dbg && blockIdx.x == 0 && it < 64 && lane == 0) {
                 dbg[it * 8 + 0] = c0; dbg[it * 8 + 1] = c1; dbg[it * 8 + 2] = c2; dbg[it * 8 + 3] = c3;
                 dbg[it * 8 + 4] = clock64();
             }
-            tcur = tnext;
         }
         tma::bulk_wait0();
     } else {
         // ================= compute warps =================
         const int ctid = tid - 32, ncth = 32 * SHORT_TMA_COMPUTE_WARPS;
-        for (int it = 0; it < count; ++it) {
+        for (int it = 0;; ++it) {
             const int s = it % NS;
             const unsigned ph = (unsigned)((it / NS) & 1);
-            const TileS t = tiles[blockIdx.x + (long long)it * gridDim.x];
             const long long w0 = clock64();
             tma::mbar_wait(tma::smem_u32(&bars[s]), ph);
             const long long w1 = clock64();
+            const int P = sdesc[s].P, nr = sdesc[s].nr;
+            if (P < 0) break;
             double* xs = ring + (size_t)s * prm.stage_doubles;
-            switch (t.P) {
-                case 0: short_tile_compute<K, 0>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
-                case 1: if constexpr (ShortDims<K>::pmax() >= 1) short_tile_compute<K, 1>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
-                case 2: if constexpr (ShortDims<K>::pmax() >= 2) short_tile_compute<K, 2>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
-                case 3: if constexpr (ShortDims<K>::pmax() >= 3) short_tile_compute<K, 3>(xs, hd, t.nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+            switch (P) {
+                case 0: short_tile_compute<K, 0>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 1: if constexpr (ShortDims<K>::pmax() >= 1) short_tile_compute<K, 1>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 2: if constexpr (ShortDims<K>::pmax() >= 2) short_tile_compute<K, 2>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 3: if constexpr (ShortDims<K>::pmax() >= 3) short_tile_compute<K, 3>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
             }
             tma::fence_proxy_async();
             __syncwarp();
@@ -524,7 +546,7 @@ struct TileLong {
 };
 
 constexpr int LONG_CH = 8;      // records per ring chunk
-constexpr int LONG_NBUF = 3;    // ring depth
+constexpr int LONG_NBUF = 4;    // ring depth
 
 template <int K>
 struct LongRec {
@@ -566,7 +588,9 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     const int PT = nr * PIt;            // poles in the tile (<= 32)
     const int TL = K * PIt;
     double* xs = reinterpret_cast<double*>(smraw);                                  // NP * 32
-    unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + (size_t)warp * WARP_BYTES;
+    long long* caddr = reinterpret_cast<long long*>(smraw + (size_t)NP * 32 * 8);   // NQ * nr cell offsets
+    const int caddr_bytes = (NQ * nr * 8 + 15) & ~15;
+    unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + caddr_bytes + (size_t)warp * WARP_BYTES;
     unsigned char* ring = wbase;
     double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * CHB);
 
@@ -595,14 +619,20 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     }
     issue_chunk(c_first);
     issue_chunk(c_first + 1);
+    issue_chunk(c_first + 2);
     __syncthreads();
     const int S = sS;
+    const int ncell = NQ * nr;
+    for (int c = tid; c < ncell; c += nth) {
+        const int qq = c / nr, r = c - qq * nr;
+        caddr[c] = cell_addr(sbase, S, qq, t.r0 + r, KDp);
+    }
+    __syncthreads();
 
     // ---- stage the x tile in (asynchronous 8-byte copies, transposed to xs[row][pole])
-    const int ncell = NQ * nr;
     for (int c = warp; c < ncell; c += nwarp) {
         const int qq = c / nr, r = c - qq * nr;
-        const double* src = X + cell_addr(sbase, S, qq, t.r0 + r, KDp);
+        const double* src = X + caddr[c];
         const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + (size_t)qq * K * 32 + r * PIt);
         for (int tt = lane; tt < TL; tt += 32) cp_async8(dst + tab_row[tt] * 8, src + tab_g[tt]);
     }
@@ -616,8 +646,8 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
 #pragma unroll
     for (int m = 0; m < K; ++m) acc[m] = 0.0;
     for (int c = c_first; c <= c_last; ++c) {
-        issue_chunk(c + 2);
-        cp_async_wait<2>();            // chunk c has landed (this thread's copies) ...
+        issue_chunk(c + 3);
+        cp_async_wait<3>();            // chunk c has landed (this thread's copies) ...
         __syncwarp();                  // ... and every lane's
         const unsigned char* buf = ring + (c % LONG_NBUF) * CHB;
         const int lo = max(b0, c * LONG_CH) - c * LONG_CH, hi = min(b1, (c + 1) * LONG_CH) - c * LONG_CH;
@@ -641,7 +671,7 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
                 }
                 __syncwarp();
                 for (int r = 0; r < nr; ++r) {
-                    double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
+                    double* dstg = Y + caddr[q * nr + r];
                     const double* sc = scratch + r * PIt;
                     if (beta == 0.0) {
                         for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
@@ -657,7 +687,7 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
                 for (int m = 0; m < K; ++m) acc[m] = 0.0;
             }
         }
-        __syncwarp();                  // chunk buffer may be refilled two iterations later
+        __syncwarp();                  // the chunk buffer is refilled by the next iteration's issue
     }
     cp_async_wait<0>();
 }

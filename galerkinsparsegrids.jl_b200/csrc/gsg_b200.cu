@@ -131,7 +131,8 @@ struct gsg_plan {
     int htotal = 0, short_pmax = -1;
     // long kernel: per p, the principal sub-block as a compact stream of block records
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
-    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
+    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each row tile (+ end)
+    int long_TC = 0;                                             // 1-D cells per tile of the long kernel
 
     std::vector<Direction> dirs;
 
@@ -224,40 +225,50 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
 
-    // long kernel: per p the principal sub-block (rows and columns < 2^p) as a stream of block
-    // records {K*K values row-major, int col, int flags (bit 0 = last record of its block-row)};
-    // every row owns at least one record so the end-of-row flag always exists
+    // long kernel: per p the principal sub-block (rows and columns < K*2^p) cut into T x T tiles
+    // (T = TC*K); tiles holding a stored entry become dense records {T*T values row-major,
+    // int col_tile, int flags (bit 0 = last record of its row tile), pad}; every row tile owns at
+    // least one record so the end-of-row flag always exists
     P.lrec.resize(n + 1);
     P.lrow_start.assign(n + 1, {});
-    {
-        const int KK = K * K;
-        const int REC = (KK * 8 + 8 + 15) & ~15;
+    if (K <= 5) {
+        const int TC = K == 1 ? 16 : (K == 2 ? 8 : (K <= 4 ? 4 : 2));
+        const int T = TC * K;
+        const int REC = T * T * 8 + 16;
+        P.long_TC = TC;
         for (int p = 0; p <= n; ++p) {
             const int nq = 1 << p;
+            if (nq < TC) continue;
+            const int nt = nq / TC;
             std::vector<unsigned char> buf;
             std::vector<int>& rs = P.lrow_start[p];
-            rs.assign(nq + 1, 0);
+            rs.assign(nt + 1, 0);
             int nrec = 0;
-            for (int q = 0; q < nq; ++q) {
-                rs[q] = nrec;
-                int cnt = 0;
-                for (int b = rowptr[q]; b < rowptr[q + 1] && col[b] < nq; ++b) ++cnt;
-                const int emit = std::max(cnt, 1);
-                for (int i = 0; i < emit; ++i) {
+            for (int R = 0; R < nt; ++R) {
+                rs[R] = nrec;
+                std::vector<int> cols;
+                for (int Cc = 0; Cc < nt; ++Cc) {
+                    bool any = false;
+                    for (int qa = 0; qa < TC && !any; ++qa)
+                        for (int qb = 0; qb < TC && !any; ++qb)
+                            any = blk[(size_t)(R * TC + qa) * NQ + (Cc * TC + qb)] != 0;
+                    if (any) cols.push_back(Cc);
+                }
+                if (cols.empty()) cols.push_back(0);          // dummy zero tile carries the flag
+                for (size_t i = 0; i < cols.size(); ++i) {
                     buf.resize((size_t)(nrec + 1) * REC, 0);
                     unsigned char* rec = buf.data() + (size_t)nrec * REC;
-                    int meta[2] = {0, i == emit - 1 ? 1 : 0};
-                    if (i < cnt) {
-                        const int b = rowptr[q] + i;
-                        std::memcpy(rec, val.data() + (size_t)b * P.KK2, (size_t)KK * 8);
-                        meta[0] = col[b];
-                    }
-                    std::memcpy(rec + KK * 8, meta, 8);
+                    double* v = reinterpret_cast<double*>(rec);
+                    for (int a = 0; a < T; ++a)
+                        for (int c2 = 0; c2 < T; ++c2)
+                            v[a * T + c2] = Hd[(size_t)(R * T + a) * N1 + (cols[i] * T + c2)];
+                    int meta[2] = {cols[i], i + 1 == cols.size() ? 1 : 0};
+                    std::memcpy(rec + (size_t)T * T * 8, meta, 8);
                     ++nrec;
                 }
             }
-            rs[nq] = nrec;
-            buf.resize((size_t)(nrec + 2 * LONG_CH) * REC, 0);     // over-read slack for whole-chunk copies
+            rs[nt] = nrec;
+            buf.resize((size_t)(nrec + LONG_NBUF) * REC, 0);     // slack
             P.lrec[p].reset(new DevBuf<unsigned char>());
             GSG_TRY(P.lrec[p]->upload(buf));
         }
@@ -296,6 +307,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
 
     // groups keyed by the other dims' levels, in layout order of their level_d = 0 block
     std::vector<GroupDev> groups;
+    const int slab_only = getenv("GSG_SLAB_L6") ? atoi(getenv("GSG_SLAB_L6")) : -1;   // experiment: L2-resident slabs
     for (const gsg::Block& b0 : S.blocks) {
         if (b0.level[d] != 0) continue;
         GroupDev g;
@@ -316,6 +328,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         if (Slo * Shi > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many items in a pole group");
         g.S = (int)Slo;
         g.nitems = (int)(Slo * Shi);
+        if (slab_only >= 0 && d != D - 1 && b0.level[D - 1] != slab_only) g.nitems = 0;
         groups.push_back(g);
     }
     GSG_TRY(dir.groups.upload(groups));
@@ -370,17 +383,18 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
-        const int REC = (K * K * 8 + 8 + 15) & ~15;
-        const size_t warp_bytes = (size_t)LONG_NBUF * LONG_CH * REC + (size_t)K * 32 * 8;
-        int nw = NQ >= 64 ? 16 : (NQ >= 16 ? 8 : 4);
+        const int TCl = std::max(1, P.long_TC), Tl = TCl * K;
+        const size_t warp_bytes = (size_t)LONG_NBUF * ((size_t)Tl * Tl * 8 + 16) + (size_t)K * 32 * 8;
+        const int nt_rows = NQ / TCl;                       // row tiles of this class
+        int nw = std::max(1, std::min(16, nt_rows));
         const int nr_long = PI >= 32 ? 1 : 32 / PI;
         const size_t tile_bytes = (size_t)NP * 32 * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
-        while (nw > 2 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw -= (nw > 8 ? 4 : nw / 2);
+        while (nw > 1 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw = (nw > 4 ? nw - 4 : nw / 2);
         const size_t long_smem = tile_bytes + nw * warp_bytes;
         if (short_supported(K, p)) {
             if (tma_active) continue;
             c.kind = Kind::SHORT;
-        } else if (K <= 5 && long_smem + 2048 <= SMEM_OPTIN_MAX) {
+        } else if (K <= 5 && NQ >= TCl && P.lrec[p] && long_smem + 2048 <= SMEM_OPTIN_MAX) {
             c.kind = Kind::LONG;
         } else {
             c.kind = Kind::GENERIC;
@@ -413,23 +427,24 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             if (ll.empty()) continue;
             // row parts: enough CTAs to cover the GPU twice, but at least ~32 records per warp
             const std::vector<int>& rs = P.lrow_start[p];
-            const int nrec = rs[NQ];
+            const int NRT = nt_rows;                      // row tiles
+            const int nrec = rs[NRT];
             // row parts: one CTA per pole set is enough (its warps stream ~nrec/nw records each from
             // the cp.async ring); only split when a class would otherwise occupy fewer than 16 SMs
             int rsplit = 1;
             if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
-            else if ((long long)ll.size() < 16) rsplit = (int)std::min<long long>(16 / (long long)ll.size(), std::max(1, nrec / (nw * 64)));
+            else if ((long long)ll.size() < 32) rsplit = (int)std::min<long long>(32 / (long long)ll.size(), std::max(1, nrec / (nw * 8)));
             rsplit = std::max(1, std::min(rsplit, 64));
             c.rsplit = rsplit;
             const int G = rsplit * nw;
-            std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
+            std::vector<int> pb(G + 1, nrec), pr(G + 1, NRT);
             pb[0] = 0; pr[0] = 0;
             {
-                const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
+                const long long total = (long long)nrec + NRT;      // +1 per row tile: epilogue cost
                 int q = 0;
                 for (int g = 1; g < G; ++g) {
                     const long long target = total * g / G;
-                    while (q < NQ && (long long)rs[q] + q < target) ++q;
+                    while (q < NRT && (long long)rs[q] + q < target) ++q;
                     pr[g] = std::max(q, pr[g - 1]);
                     pb[g] = rs[pr[g]];
                 }

@@ -526,15 +526,17 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// Long poles (p >= 4 at k = 3): lanes = poles.  A tile holds PT <= 32 poles (a sub-range
-// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles) and
-// one ROW PART of the principal sub-block; the whole x tile sits in shared memory as xs[row][32]
-// (conflict-free for lanes = poles).  The matrix of class p is a compact stream of K x K block
-// records (values, block column, end-of-row flag) in row order.  Every warp owns a contiguous
-// range of whole block-rows (host partition balanced in block count) and streams its records
-// through a private 3-deep cp.async ring in shared memory, so no L2 latency is exposed in the
-// inner loop: per record 5 broadcast LDS.128 + K conflict-free LDS.64 of x + K*K DFMAs.  Each
-// finished block-row goes through a per-warp scratch so the global write is coalesced.
+// Long poles (p >= 4 at k = 3): lanes = poles, dense TILE stream.  A CTA tile holds PT <= 32
+// poles (a sub-range a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item
+// has few poles); the whole x tile sits in shared memory as xs[row][32] (conflict-free for
+// lanes = poles).  The principal sub-block of class p is cut into T x T tiles (T = TC*K rows,
+// TC 1-D cells; 12 x 12 at k = 3); only tiles with a stored entry are kept, as a stream of
+// dense records {T*T values, column tile, end-of-row flag} in row-tile order (25 % of the tiles
+// at p = 8, all of them at p = 4).  Every warp owns a contiguous range of row tiles (host
+// partition balanced in record count) and streams its records through a private cp.async ring
+// in shared memory: per record T conflict-free LDS.64 of x, T*T/2 broadcast LDS.128 of the
+// tile and T*T DFMAs on T independent accumulators.  Each finished row tile goes cell by cell
+// through a per-warp scratch so the global write is coalesced.
 //   in-item order t -> a = t % na, m = (t / na) % K, bl = t / (K*na):
 //   pole = a + na*bl, in-cell offset = ebase + a + A*m + K*A*bl.
 // ------------------------------------------------------------------------------------------
@@ -545,13 +547,13 @@ struct TileLong {
     short nr, na, nb, part;   // part: which row part of the matrix this CTA computes
 };
 
-constexpr int LONG_CH = 8;      // records per ring chunk
-constexpr int LONG_NBUF = 4;    // ring depth
+constexpr int LONG_NBUF = 4;    // ring depth (records in flight per warp)
 
 template <int K>
-struct LongRec {
-    static constexpr int KK = K * K;
-    static constexpr int BYTES = (KK * 8 + 8 + 15) & ~15;     // values + {col, flags}, 16-byte multiple
+struct LongTile {
+    static constexpr int TC = K == 1 ? 16 : (K == 2 ? 8 : (K <= 4 ? 4 : 2));   // 1-D cells per tile
+    static constexpr int T = TC * K;                                            // rows = cols per tile
+    static constexpr int BYTES = T * T * 8 + 16;                                // values + {col tile, flags}
 };
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
@@ -568,11 +570,10 @@ template <int K>
 __global__ void __launch_bounds__(512)
 sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
                   const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles,
-                  const unsigned char* __restrict__ recs, const int* __restrict__ partBlk,
+                  const unsigned char* __restrict__ recs, const int* __restrict__ partRec,
                   const int* __restrict__ partRow, int p, int KDp, int A) {
-    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
-    constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
-    constexpr int WARP_BYTES = LONG_NBUF * CHB + K * 32 * 8;  // ring + scratch per warp
+    constexpr int TC = LongTile<K>::TC, T = LongTile<K>::T, REC = LongTile<K>::BYTES;
+    constexpr int WARP_BYTES = LONG_NBUF * REC + K * 32 * 8;  // ring + scratch per warp
     const int NQ = 1 << p, NP = K * NQ;
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ long long sbase[MAXL + 1];
@@ -592,19 +593,18 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     const int caddr_bytes = (NQ * nr * 8 + 15) & ~15;
     unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + caddr_bytes + (size_t)warp * WARP_BYTES;
     unsigned char* ring = wbase;
-    double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * CHB);
+    double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * REC);
 
-    // this warp's records [b0, b1) and first block-row q
+    // this warp's records [b0, b1) and first row tile
     const int gpart = t.part * nwarp + warp;
-    const int b0 = partBlk[gpart], b1 = partBlk[gpart + 1];
-    int q = partRow[gpart];
-    const int c_first = b0 / LONG_CH, c_last = b1 > b0 ? (b1 - 1) / LONG_CH : c_first - 1;
+    const int b0 = partRec[gpart], b1 = partRec[gpart + 1];
+    int rt = partRow[gpart];
 
-    auto issue_chunk = [&](int c) {
-        if (c <= c_last) {
-            const unsigned char* src = recs + (size_t)c * CHB;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (c % LONG_NBUF) * CHB);
-            for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
+    auto issue_rec = [&](int b) {
+        if (b < b1) {
+            const unsigned char* src = recs + (size_t)b * REC;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (b % LONG_NBUF) * REC);
+            for (int g = lane; g < REC / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
         }
         cp_async_commit();
     };
@@ -617,9 +617,8 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
         tab_row[tt] = (short)(m * 32 + a + na * bl);
         tab_g[tt] = t.ebase + a + A * m + K * A * bl;
     }
-    issue_chunk(c_first);
-    issue_chunk(c_first + 1);
-    issue_chunk(c_first + 2);
+#pragma unroll
+    for (int i = 0; i < LONG_NBUF - 1; ++i) issue_rec(b0 + i);
     __syncthreads();
     const int S = sS;
     const int ncell = NQ * nr;
@@ -640,34 +639,39 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     cp_async_wait<0>();
     __syncthreads();
 
-    // ---- stream this warp's block records
+    // ---- stream this warp's tile records
     const bool active = lane < PT;
-    double acc[K];
+    double acc[T];
 #pragma unroll
-    for (int m = 0; m < K; ++m) acc[m] = 0.0;
-    for (int c = c_first; c <= c_last; ++c) {
-        issue_chunk(c + 3);
-        cp_async_wait<3>();            // chunk c has landed (this thread's copies) ...
-        __syncwarp();                  // ... and every lane's
-        const unsigned char* buf = ring + (c % LONG_NBUF) * CHB;
-        const int lo = max(b0, c * LONG_CH) - c * LONG_CH, hi = min(b1, (c + 1) * LONG_CH) - c * LONG_CH;
-        for (int i = lo; i < hi; ++i) {
-            const unsigned char* rec = buf + i * REC;
-            const int2 meta = *reinterpret_cast<const int2*>(rec + KK * 8);
-            const double* hv = reinterpret_cast<const double*>(rec);
-            const double* xv = xs + (size_t)meta.x * K * 32 + lane;
-            double xr[K];
+    for (int i = 0; i < T; ++i) acc[i] = 0.0;
+    for (int b = b0; b < b1; ++b) {
+        issue_rec(b + LONG_NBUF - 1);
+        cp_async_wait<LONG_NBUF - 1>();    // record b has landed (this thread's copies) ...
+        __syncwarp();                      // ... and every lane's
+        const unsigned char* rec = ring + (b % LONG_NBUF) * REC;
+        const int2 meta = *reinterpret_cast<const int2*>(rec + T * T * 8);
+        const double* xv = xs + (size_t)meta.x * T * 32 + lane;
+        double xr[T];
 #pragma unroll
-            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[mi * 32];
+        for (int j = 0; j < T; ++j) xr[j] = xv[j * 32];
+        const double2* hv = reinterpret_cast<const double2*>(rec);
 #pragma unroll
-            for (int mo = 0; mo < K; ++mo)
+        for (int i = 0; i < T; ++i) {
 #pragma unroll
-                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(hv[mo * K + mi], xr[mi], acc[mo]);
-            if (meta.y & 1) {          // end of block-row q: coalesced write through the scratch
+            for (int j = 0; j < T; j += 2) {
+                const double2 h2 = hv[(i * T + j) / 2];
+                acc[i] = fma(h2.x, xr[j], acc[i]);
+                acc[i] = fma(h2.y, xr[j + 1], acc[i]);
+            }
+        }
+        if (meta.y & 1) {              // end of row tile rt: coalesced write, one 1-D cell at a time
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) {
+                const int q = rt * TC + cc;
                 __syncwarp();
                 if (active) {
 #pragma unroll
-                    for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
+                    for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[cc * K + m];
                 }
                 __syncwarp();
                 for (int r = 0; r < nr; ++r) {
@@ -682,12 +686,12 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
                         }
                     }
                 }
-                ++q;
-#pragma unroll
-                for (int m = 0; m < K; ++m) acc[m] = 0.0;
             }
+            ++rt;
+#pragma unroll
+            for (int i = 0; i < T; ++i) acc[i] = 0.0;
         }
-        __syncwarp();                  // the chunk buffer is refilled by the next iteration's issue
+        __syncwarp();                  // the ring slot is refilled by the next iteration's issue
     }
     cp_async_wait<0>();
 }

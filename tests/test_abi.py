@@ -1,0 +1,95 @@
+"""CPU-side checks of the product: the C-ABI library loads, exports every symbol include/gsg_b200.h
+declares, fails loudly (no CPU fallback) without a GPU, and its host-side setup mirrors agree with
+the oracle.  No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import f_sin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gsg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsg_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(gsg):
+    lib = ctypes.CDLL(gsg.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # the Python binding declares exactly the header's functions
+    assert sorted(gsg.SIGNATURES) == names
+
+
+def test_no_cpu_fallback(gsg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(gsg.GsgError) as ei:
+        gsg.Plan(2, 3, 3)
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "galerkinsparsegrids.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "gsg_oracle" not in src and "cbaseline" not in src, f
+
+
+def test_host_setup_matches_oracle(gsg, oracle):
+    """The library's own host-side setup (what a Julia host computes itself) against the oracle:
+    basis tables bit-exact, H = periodic_DLF_matrix to rounding (same pattern)."""
+    leg, dg = gsg.basis_tables(3)
+    assert np.array_equal(leg, np.array(oracle.leg_coeffs()))
+    assert np.array_equal(dg, np.array(oracle.dg_coeffs(3)))
+    for k, n in [(3, 5), (2, 4), (4, 3), (1, 3), (5, 2)]:
+        H = gsg.periodic_DLF_matrix(k, n)
+        Ho = oracle.periodic_DLF_matrix(k, n)
+        assert H.nnz == Ho.nnz and np.array_equal(H.indices, Ho.rowval) and np.array_equal(H.indptr, Ho.colptr)
+        assert np.abs(H.data - Ho.nzval).max() <= 4e-15 * np.abs(Ho.nzval).max()
+    Hp = gsg.periodic_DLF_matrix(3, 3, basis="pos").toarray()
+    assert np.abs(Hp - oracle.periodic_DLF_matrix(3, 3, "pos").toarray()).max() < 1e-12
+
+
+def test_layout_mirrors(gsg, oracle):
+    for D, k, n, scheme in [(2, 2, 3, "sparse"), (2, 3, 2, "full"), (3, 2, 2, "sparse")]:
+        assert gsg.get_size(D, k, n, scheme) == oracle.get_size(D, k, n, scheme)
+        assert gsg.V2Dref(D, k, n, scheme) == oracle.V2Dref(D, k, n, scheme)
+        vect = np.random.default_rng(3).standard_normal(gsg.get_size(D, k, n, scheme))
+        d = gsg.V2D(D, k, n, vect, scheme)
+        assert np.array_equal(gsg.D2V(D, k, n, d, scheme), vect)          # test/vhier_DG.jl round trip
+    assert [gsg.cell_index(0.3, l) for l in range(1, 6)] == [1, 1, 2, 3, 5]   # test/elementary.jl:17-27
+    assert gsg.cell_index(1.3, 4) == 8
+
+
+def test_projection_and_tensor_construct(gsg, oracle):
+    v_o = oracle.coeffs_1d(3, 4, f_sin)
+    v_g = gsg.vcoeffs_DG(1, 3, 4, f_sin)
+    assert np.abs(v_o - v_g).max() < 1e-15
+    t_o = oracle.tensor_construct(3, 3, 3, [v_o[:24]] * 3)
+    t_g = gsg.tensor_construct(3, 3, 3, [v_o[:24]] * 3)
+    assert np.array_equal(t_o, t_g)
+    x = np.linspace(-0.2, 1.2, 57)
+    for (level, cell, mode) in [(0, 1, 1), (0, 1, 3), (1, 1, 2), (3, 2, 3), (4, 8, 1)]:
+        ref = np.array([oracle.v(3, level, cell, mode, float(xi)) for xi in x])
+        assert np.array_equal(gsg.basis_v(3, level, cell, mode, x), ref)
+
+
+def test_argument_errors(gsg):
+    with pytest.raises(ValueError):
+        gsg.get_size(2, 3, 3, scheme="energy")           # unknown scheme -> ArgumentError
+    with pytest.raises(gsg.GsgError):
+        gsg.get_size(2, 11, 3)                           # k > K_max -> DomainError
+    with pytest.raises(ValueError):
+        gsg.periodic_DLF_matrix(3, 3, basis="nodal")     # broken in the reference as well

@@ -95,6 +95,7 @@ struct SweepClass {          // one launch of a sweep
     int NPOLE = 0, Amin = 0; // generic kernel parameters
     int nwarps = 8;          // long kernel: warps per CTA
     int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
+    int nbuf = 4;            // long kernel: record ring depth
     DevBuf<int> partBlk, partRow;
     size_t smem = 0;
     DevBuf<TileDev> tiles;
@@ -132,7 +133,7 @@ struct gsg_plan {
     // long kernel: per p, the principal sub-block as a compact stream of block records
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
     std::vector<std::vector<int>> lrow_start;                    // index p: first record of each row tile (+ end)
-    int long_TC = 0;                                             // 1-D cells per tile of the long kernel
+    int long_TR = 0;                                             // rows per tile of the long kernel
 
     std::vector<Direction> dirs;
 
@@ -225,33 +226,34 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
 
-    // long kernel: per p the principal sub-block (rows and columns < K*2^p) cut into T x T tiles
-    // (T = TC*K); tiles holding a stored entry become dense records {T*T values row-major,
-    // int col_tile, int flags (bit 0 = last record of its row tile), pad}; every row tile owns at
+    // long kernel: per p the principal sub-block (rows and columns < K*2^p) cut into TR x TCc
+    // tiles; tiles holding a stored entry become dense records in mma.m8n8k4 A-fragment order
+    // (for each 8x4 fragment (mb, kb): lane l holds H[mb*8 + l/4][kb*4 + l%4]) followed by
+    // {int col_tile, int flags (bit 0 = last record of its row tile), pad}; every row tile owns at
     // least one record so the end-of-row flag always exists
     P.lrec.resize(n + 1);
     P.lrow_start.assign(n + 1, {});
     if (K <= 5) {
-        const int TC = K == 1 ? 16 : (K == 2 ? 8 : (K <= 4 ? 4 : 2));
-        const int T = TC * K;
-        const int REC = T * T * 8 + 16;
-        P.long_TC = TC;
+        const int TR = (K == 3) ? 24 : (K == 5 ? 40 : 16), TCc = TR / 2;
+        const int MB = TR / 8, KB = TCc / 4;
+        const int REC = TR * TCc * 8 + 16;
+        P.long_TR = TR;
         for (int p = 0; p <= n; ++p) {
-            const int nq = 1 << p;
-            if (nq < TC) continue;
-            const int nt = nq / TC;
+            const int NP = K << p;
+            if (NP % TR != 0) continue;
+            const int ntr = NP / TR, ntc = NP / TCc;
             std::vector<unsigned char> buf;
             std::vector<int>& rs = P.lrow_start[p];
-            rs.assign(nt + 1, 0);
+            rs.assign(ntr + 1, 0);
             int nrec = 0;
-            for (int R = 0; R < nt; ++R) {
+            for (int R = 0; R < ntr; ++R) {
                 rs[R] = nrec;
                 std::vector<int> cols;
-                for (int Cc = 0; Cc < nt; ++Cc) {
+                for (int Cc = 0; Cc < ntc; ++Cc) {
                     bool any = false;
-                    for (int qa = 0; qa < TC && !any; ++qa)
-                        for (int qb = 0; qb < TC && !any; ++qb)
-                            any = blk[(size_t)(R * TC + qa) * NQ + (Cc * TC + qb)] != 0;
+                    for (int a = 0; a < TR && !any; ++a)
+                        for (int c2 = 0; c2 < TCc && !any; ++c2)
+                            any = Hd[(size_t)(R * TR + a) * N1 + (Cc * TCc + c2)] != 0.0;
                     if (any) cols.push_back(Cc);
                 }
                 if (cols.empty()) cols.push_back(0);          // dummy zero tile carries the flag
@@ -259,16 +261,18 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
                     buf.resize((size_t)(nrec + 1) * REC, 0);
                     unsigned char* rec = buf.data() + (size_t)nrec * REC;
                     double* v = reinterpret_cast<double*>(rec);
-                    for (int a = 0; a < T; ++a)
-                        for (int c2 = 0; c2 < T; ++c2)
-                            v[a * T + c2] = Hd[(size_t)(R * T + a) * N1 + (cols[i] * T + c2)];
+                    for (int mb = 0; mb < MB; ++mb)
+                        for (int kb = 0; kb < KB; ++kb)
+                            for (int l = 0; l < 32; ++l)
+                                v[(mb * KB + kb) * 32 + l] =
+                                    Hd[(size_t)(R * TR + mb * 8 + l / 4) * N1 + (cols[i] * TCc + kb * 4 + l % 4)];
                     int meta[2] = {cols[i], i + 1 == cols.size() ? 1 : 0};
-                    std::memcpy(rec + (size_t)T * T * 8, meta, 8);
+                    std::memcpy(rec + (size_t)TR * TCc * 8, meta, 8);
                     ++nrec;
                 }
             }
-            rs[nt] = nrec;
-            buf.resize((size_t)(nrec + LONG_NBUF) * REC, 0);     // slack
+            rs[ntr] = nrec;
+            buf.resize((size_t)(nrec + 8) * REC, 0);     // slack
             P.lrec[p].reset(new DevBuf<unsigned char>());
             GSG_TRY(P.lrec[p]->upload(buf));
         }
@@ -383,18 +387,22 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
-        const int TCl = std::max(1, P.long_TC), Tl = TCl * K;
-        const size_t warp_bytes = (size_t)LONG_NBUF * ((size_t)Tl * Tl * 8 + 16) + (size_t)K * 32 * 8;
-        const int nt_rows = NQ / TCl;                       // row tiles of this class
-        int nw = std::max(1, std::min(16, nt_rows));
+        const int TRl = std::max(8, P.long_TR), TCl = TRl / 2;
+        const size_t rec_bytes = (size_t)TRl * TCl * 8 + 16;
+        const size_t scratch_bytes = (size_t)TRl * 32 * 8;
+        const int nt_rows = (NP % TRl == 0) ? NP / TRl : 0;   // row tiles of this class
         const int nr_long = PI >= 32 ? 1 : 32 / PI;
-        const size_t tile_bytes = (size_t)NP * 32 * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
-        while (nw > 1 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw = (nw > 4 ? nw - 4 : nw / 2);
-        const size_t long_smem = tile_bytes + nw * warp_bytes;
+        const size_t xs_stride = (size_t)((NP + 27) / 32) * 32 + 4;
+        const size_t tile_bytes = 32 * xs_stride * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
+        int nw = std::max(1, std::min(8, nt_rows));
+        int nbuf = 4;
+        while (nw > 1 && tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes) + 2048 > SMEM_OPTIN_MAX) nw /= 2;
+        if (tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes) + 2048 > SMEM_OPTIN_MAX) nbuf = 2;
+        const size_t long_smem = tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes);
         if (short_supported(K, p)) {
             if (tma_active) continue;
             c.kind = Kind::SHORT;
-        } else if (K <= 5 && NQ >= TCl && P.lrec[p] && long_smem + 2048 <= SMEM_OPTIN_MAX) {
+        } else if (K <= 5 && nt_rows > 0 && P.lrec[p] && long_smem + 2048 <= SMEM_OPTIN_MAX) {
             c.kind = Kind::LONG;
         } else {
             c.kind = Kind::GENERIC;
@@ -402,6 +410,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         if (c.kind == Kind::LONG) {
             std::vector<TileLong> ll;
             c.nwarps = nw;
+            c.nbuf = nbuf;
             c.smem = long_smem;
             const int A = dir.A, B = PI / A;
             for (size_t gi = 0; gi < groups.size(); ++gi) {
@@ -433,7 +442,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             // the cp.async ring); only split when a class would otherwise occupy fewer than 16 SMs
             int rsplit = 1;
             if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
-            else if ((long long)ll.size() < 32) rsplit = (int)std::min<long long>(32 / (long long)ll.size(), std::max(1, nrec / (nw * 8)));
+            else if ((long long)ll.size() * nw < 256) rsplit = (int)std::min<long long>(256 / ((long long)ll.size() * nw), std::max(1, nrec / (nw * 4)));
             rsplit = std::max(1, std::min(rsplit, 64));
             c.rsplit = rsplit;
             const int G = rsplit * nw;
@@ -538,7 +547,7 @@ int launch_check(const char* what, int K, const SweepClass& c) {
 
 template <class Kern>
 int ensure_smem(Kern kern, size_t smem, size_t& configured) {
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 32 * 1024 && smem > configured) {      // static + dynamic must stay under 48 KB without opt-in
         GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
@@ -611,14 +620,22 @@ template <int K>
 int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                   double* y, double alpha, double beta) {
     if constexpr (K >= 1 && K <= 5) {
-        auto kern = sweep_long_kernel<K>;
-        static thread_local size_t configured = 0;
-        GSG_TRY(ensure_smem(kern, c.smem, configured));
         int tb, tn;
         tile_range(pl, c.ntiles, tb, tn);
         if (tn == 0) return 0;
-        kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
-                                                 c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
+        if (c.nbuf == 4) {
+            auto kern = sweep_long_kernel<K, 4>;
+            static thread_local size_t configured = 0;
+            GSG_TRY(ensure_smem(kern, c.smem, configured));
+            kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
+                                                     c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
+        } else {
+            auto kern = sweep_long_kernel<K, 2>;
+            static thread_local size_t configured = 0;
+            GSG_TRY(ensure_smem(kern, c.smem, configured));
+            kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
+                                                     c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_long", K, c);
     }

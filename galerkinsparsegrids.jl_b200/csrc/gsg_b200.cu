@@ -95,7 +95,6 @@ struct SweepClass {          // one launch of a sweep
     int NPOLE = 0, Amin = 0; // generic kernel parameters
     int nwarps = 8;          // long kernel: warps per CTA
     int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
-    int nbuf = 4;            // long kernel: record ring depth
     DevBuf<int> partBlk, partRow;
     size_t smem = 0;
     DevBuf<TileDev> tiles;
@@ -132,8 +131,7 @@ struct gsg_plan {
     int htotal = 0, short_pmax = -1;
     // long kernel: per p, the principal sub-block as a compact stream of block records
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
-    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each row tile (+ end)
-    int long_TR = 0;                                             // rows per tile of the long kernel
+    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
 
     std::vector<Direction> dirs;
 
@@ -226,53 +224,40 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
 
-    // long kernel: per p the principal sub-block (rows and columns < K*2^p) cut into TR x TCc
-    // tiles; tiles holding a stored entry become dense records in mma.m8n8k4 A-fragment order
-    // (for each 8x4 fragment (mb, kb): lane l holds H[mb*8 + l/4][kb*4 + l%4]) followed by
-    // {int col_tile, int flags (bit 0 = last record of its row tile), pad}; every row tile owns at
-    // least one record so the end-of-row flag always exists
+    // long kernel: per p the principal sub-block (rows and columns < 2^p) as a stream of block
+    // records {K*K values row-major, int col, int flags (bit 0 = last record of its block-row)};
+    // every row owns at least one record so the end-of-row flag always exists
     P.lrec.resize(n + 1);
     P.lrow_start.assign(n + 1, {});
-    if (K <= 5) {
-        const int TR = (K == 3) ? 24 : (K == 5 ? 40 : 16), TCc = TR / 2;
-        const int MB = TR / 8, KB = TCc / 4;
-        const int REC = TR * TCc * 8 + 16;
-        P.long_TR = TR;
+    {
+        const int KK = K * K;
+        const int REC = (KK * 8 + 8 + 15) & ~15;
         for (int p = 0; p <= n; ++p) {
-            const int NP = K << p;
-            if (NP % TR != 0) continue;
-            const int ntr = NP / TR, ntc = NP / TCc;
+            const int nq = 1 << p;
             std::vector<unsigned char> buf;
             std::vector<int>& rs = P.lrow_start[p];
-            rs.assign(ntr + 1, 0);
+            rs.assign(nq + 1, 0);
             int nrec = 0;
-            for (int R = 0; R < ntr; ++R) {
-                rs[R] = nrec;
-                std::vector<int> cols;
-                for (int Cc = 0; Cc < ntc; ++Cc) {
-                    bool any = false;
-                    for (int a = 0; a < TR && !any; ++a)
-                        for (int c2 = 0; c2 < TCc && !any; ++c2)
-                            any = Hd[(size_t)(R * TR + a) * N1 + (Cc * TCc + c2)] != 0.0;
-                    if (any) cols.push_back(Cc);
-                }
-                if (cols.empty()) cols.push_back(0);          // dummy zero tile carries the flag
-                for (size_t i = 0; i < cols.size(); ++i) {
+            for (int q = 0; q < nq; ++q) {
+                rs[q] = nrec;
+                int cnt = 0;
+                for (int b = rowptr[q]; b < rowptr[q + 1] && col[b] < nq; ++b) ++cnt;
+                const int emit = std::max(cnt, 1);
+                for (int i = 0; i < emit; ++i) {
                     buf.resize((size_t)(nrec + 1) * REC, 0);
                     unsigned char* rec = buf.data() + (size_t)nrec * REC;
-                    double* v = reinterpret_cast<double*>(rec);
-                    for (int mb = 0; mb < MB; ++mb)
-                        for (int kb = 0; kb < KB; ++kb)
-                            for (int l = 0; l < 32; ++l)
-                                v[(mb * KB + kb) * 32 + l] =
-                                    Hd[(size_t)(R * TR + mb * 8 + l / 4) * N1 + (cols[i] * TCc + kb * 4 + l % 4)];
-                    int meta[2] = {cols[i], i + 1 == cols.size() ? 1 : 0};
-                    std::memcpy(rec + (size_t)TR * TCc * 8, meta, 8);
+                    int meta[2] = {0, i == emit - 1 ? 1 : 0};
+                    if (i < cnt) {
+                        const int b = rowptr[q] + i;
+                        std::memcpy(rec, val.data() + (size_t)b * P.KK2, (size_t)KK * 8);
+                        meta[0] = col[b];
+                    }
+                    std::memcpy(rec + KK * 8, meta, 8);
                     ++nrec;
                 }
             }
-            rs[ntr] = nrec;
-            buf.resize((size_t)(nrec + 8) * REC, 0);     // slack
+            rs[nq] = nrec;
+            buf.resize((size_t)(nrec + 2 * LONG_CH) * REC, 0);     // over-read slack for whole-chunk copies
             P.lrec[p].reset(new DevBuf<unsigned char>());
             GSG_TRY(P.lrec[p]->upload(buf));
         }
@@ -311,7 +296,6 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
 
     // groups keyed by the other dims' levels, in layout order of their level_d = 0 block
     std::vector<GroupDev> groups;
-    const int slab_only = getenv("GSG_SLAB_L6") ? atoi(getenv("GSG_SLAB_L6")) : -1;   // experiment: L2-resident slabs
     for (const gsg::Block& b0 : S.blocks) {
         if (b0.level[d] != 0) continue;
         GroupDev g;
@@ -332,7 +316,6 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         if (Slo * Shi > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many items in a pole group");
         g.S = (int)Slo;
         g.nitems = (int)(Slo * Shi);
-        if (slab_only >= 0 && d != D - 1 && b0.level[D - 1] != slab_only) g.nitems = 0;
         groups.push_back(g);
     }
     GSG_TRY(dir.groups.upload(groups));
@@ -387,22 +370,17 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
-        const int TRl = std::max(8, P.long_TR), TCl = TRl / 2;
-        const size_t rec_bytes = (size_t)TRl * TCl * 8 + 16;
-        const size_t scratch_bytes = (size_t)TRl * 32 * 8;
-        const int nt_rows = (NP % TRl == 0) ? NP / TRl : 0;   // row tiles of this class
+        const int REC = (K * K * 8 + 8 + 15) & ~15;
+        const size_t warp_bytes = (size_t)LONG_NBUF * LONG_CH * REC + (size_t)K * 32 * 8;
+        int nw = NQ >= 64 ? 16 : (NQ >= 16 ? 8 : 4);
         const int nr_long = PI >= 32 ? 1 : 32 / PI;
-        const size_t xs_stride = (size_t)((NP + 27) / 32) * 32 + 4;
-        const size_t tile_bytes = 32 * xs_stride * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
-        int nw = std::max(1, std::min(8, nt_rows));
-        int nbuf = 4;
-        while (nw > 1 && tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes) + 2048 > SMEM_OPTIN_MAX) nw /= 2;
-        if (tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes) + 2048 > SMEM_OPTIN_MAX) nbuf = 2;
-        const size_t long_smem = tile_bytes + nw * (nbuf * rec_bytes + scratch_bytes);
+        const size_t tile_bytes = (size_t)NP * 32 * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
+        while (nw > 2 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw -= (nw > 8 ? 4 : nw / 2);
+        const size_t long_smem = tile_bytes + nw * warp_bytes;
         if (short_supported(K, p)) {
             if (tma_active) continue;
             c.kind = Kind::SHORT;
-        } else if (K <= 5 && nt_rows > 0 && P.lrec[p] && long_smem + 2048 <= SMEM_OPTIN_MAX) {
+        } else if (K <= 5 && long_smem + 2048 <= SMEM_OPTIN_MAX) {
             c.kind = Kind::LONG;
         } else {
             c.kind = Kind::GENERIC;
@@ -410,7 +388,6 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         if (c.kind == Kind::LONG) {
             std::vector<TileLong> ll;
             c.nwarps = nw;
-            c.nbuf = nbuf;
             c.smem = long_smem;
             const int A = dir.A, B = PI / A;
             for (size_t gi = 0; gi < groups.size(); ++gi) {
@@ -436,24 +413,23 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             if (ll.empty()) continue;
             // row parts: enough CTAs to cover the GPU twice, but at least ~32 records per warp
             const std::vector<int>& rs = P.lrow_start[p];
-            const int NRT = nt_rows;                      // row tiles
-            const int nrec = rs[NRT];
+            const int nrec = rs[NQ];
             // row parts: one CTA per pole set is enough (its warps stream ~nrec/nw records each from
             // the cp.async ring); only split when a class would otherwise occupy fewer than 16 SMs
             int rsplit = 1;
             if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
-            else if ((long long)ll.size() * nw < 256) rsplit = (int)std::min<long long>(256 / ((long long)ll.size() * nw), std::max(1, nrec / (nw * 4)));
+            else if ((long long)ll.size() < 16) rsplit = (int)std::min<long long>(16 / (long long)ll.size(), std::max(1, nrec / (nw * 64)));
             rsplit = std::max(1, std::min(rsplit, 64));
             c.rsplit = rsplit;
             const int G = rsplit * nw;
-            std::vector<int> pb(G + 1, nrec), pr(G + 1, NRT);
+            std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
             pb[0] = 0; pr[0] = 0;
             {
-                const long long total = (long long)nrec + NRT;      // +1 per row tile: epilogue cost
+                const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
                 int q = 0;
                 for (int g = 1; g < G; ++g) {
                     const long long target = total * g / G;
-                    while (q < NRT && (long long)rs[q] + q < target) ++q;
+                    while (q < NQ && (long long)rs[q] + q < target) ++q;
                     pr[g] = std::max(q, pr[g - 1]);
                     pb[g] = rs[pr[g]];
                 }
@@ -620,22 +596,14 @@ template <int K>
 int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                   double* y, double alpha, double beta) {
     if constexpr (K >= 1 && K <= 5) {
+        auto kern = sweep_long_kernel<K>;
+        static thread_local size_t configured = 0;
+        GSG_TRY(ensure_smem(kern, c.smem, configured));
         int tb, tn;
         tile_range(pl, c.ntiles, tb, tn);
         if (tn == 0) return 0;
-        if (c.nbuf == 4) {
-            auto kern = sweep_long_kernel<K, 4>;
-            static thread_local size_t configured = 0;
-            GSG_TRY(ensure_smem(kern, c.smem, configured));
-            kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
-                                                     c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
-        } else {
-            auto kern = sweep_long_kernel<K, 2>;
-            static thread_local size_t configured = 0;
-            GSG_TRY(ensure_smem(kern, c.smem, configured));
-            kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
-                                                     c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
-        }
+        kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
+                                                 c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_long", K, c);
     }

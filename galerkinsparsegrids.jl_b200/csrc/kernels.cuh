@@ -526,19 +526,15 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// Long poles (p >= 4 at k = 3): batched dense-tile mat-vecs on the fp64 tensor pipe (DMMA).
-// A CTA tile holds PT <= 32 poles (a sub-range a0..a0+na x b0..b0+nb of one item's poles, or nr
-// whole items when an item has few poles).  The x tile sits in shared memory pole-major,
-// xsT[pole][row] with a row stride = 4 (mod 32) doubles so that DMMA B-fragment loads are
-// conflict-free.  The principal sub-block of class p is cut into TR x TCc tiles (24 x 12 at
-// k = 3); tiles holding a stored entry are kept as a stream of records, pre-arranged on the host
-// in mma.m8n8k4 A-fragment order, plus {column tile, end-of-row-tile flag} (25-45 % of the tiles
-// at p = 8, all of them at p = 4).  Feeding H to scalar DFMAs from shared memory is bound by
-// the 128 B/clk LDS delivery rate (8 B per lane per FMA ~ 25 % of fp64 peak, measured); the
-// DMMA path loads every operand once per lane for 256 FMAs (~0.75 B/FMA).  Every warp owns a
-// contiguous range of row tiles (host partition balanced in record count) and streams its records
-// through a private cp.async ring; a finished row tile is written through a per-warp scratch so
-// the global write is coalesced.
+// Long poles (p >= 4 at k = 3): lanes = poles.  A tile holds PT <= 32 poles (a sub-range
+// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles) and
+// one ROW PART of the principal sub-block; the whole x tile sits in shared memory as xs[row][32]
+// (conflict-free for lanes = poles).  The matrix of class p is a compact stream of K x K block
+// records (values, block column, end-of-row flag) in row order.  Every warp owns a contiguous
+// range of whole block-rows (host partition balanced in block count) and streams its records
+// through a private 3-deep cp.async ring in shared memory, so no L2 latency is exposed in the
+// inner loop: per record 5 broadcast LDS.128 + K conflict-free LDS.64 of x + K*K DFMAs.  Each
+// finished block-row goes through a per-warp scratch so the global write is coalesced.
 //   in-item order t -> a = t % na, m = (t / na) % K, bl = t / (K*na):
 //   pole = a + na*bl, in-cell offset = ebase + a + A*m + K*A*bl.
 // ------------------------------------------------------------------------------------------
@@ -549,16 +545,14 @@ struct TileLong {
     short nr, na, nb, part;   // part: which row part of the matrix this CTA computes
 };
 
-template <int K>
-struct LongTile {
-    // rows: multiple of 8 (DMMA M) and of K (whole 1-D cells); cols: multiple of 4 (DMMA K) and K
-    static constexpr int TR = (K == 3) ? 24 : (K == 5 ? 40 : 16);
-    static constexpr int TCc = TR / 2;
-    static constexpr int MB = TR / 8, KB = TCc / 4;
-    static constexpr int BYTES = TR * TCc * 8 + 16;         // fragments + {col tile, flags, pad}
-};
+constexpr int LONG_CH = 8;      // records per ring chunk
+constexpr int LONG_NBUF = 4;    // ring depth
 
-__host__ __device__ constexpr int long_xs_stride(int NP) { return ((NP + 27) / 32) * 32 + 4; }   // = 4 (mod 32), >= NP
+template <int K>
+struct LongRec {
+    static constexpr int KK = K * K;
+    static constexpr int BYTES = (KK * 8 + 8 + 15) & ~15;     // values + {col, flags}, 16-byte multiple
+};
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -570,54 +564,47 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-template <int K, int NBUF>
-__global__ void __launch_bounds__(256, 1)
+template <int K>
+__global__ void __launch_bounds__(512)
 sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
                   const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles,
-                  const unsigned char* __restrict__ recs, const int* __restrict__ partRec,
+                  const unsigned char* __restrict__ recs, const int* __restrict__ partBlk,
                   const int* __restrict__ partRow, int p, int KDp, int A) {
-    using LT = LongTile<K>;
-    constexpr int TR = LT::TR, TCc = LT::TCc, MB = LT::MB, KB = LT::KB, REC = LT::BYTES;
-    constexpr int CPT = TR / K;                               // 1-D cells per row tile
-    constexpr int WARP_BYTES = NBUF * REC + TR * 32 * 8;      // ring + scratch[TR][32] per warp
+    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
+    constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
+    constexpr int WARP_BYTES = LONG_NBUF * CHB + K * 32 * 8;  // ring + scratch per warp
     const int NQ = 1 << p, NP = K * NQ;
-    const int XS = long_xs_stride(NP);
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ long long sbase[MAXL + 1];
     __shared__ int sS;
-    __shared__ short tab_p[K * 32];     // pole-in-item of in-item element t
-    __shared__ short tab_m[K * 32];     // mode m of in-item element t
-    __shared__ int tab_g[K * 32];       // in-cell offset of in-item element t
+    __shared__ short tab_row[K * 32];   // m*32 + pole-in-item
+    __shared__ int tab_g[K * 32];       // in-cell offset
 
     const TileLong t = tiles[blockIdx.x];
     const int tid = threadIdx.x, nth = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
     const int na = t.na, nb = t.nb, nr = t.nr;
     const int PIt = na * nb;            // poles per item in this tile
+    const int PT = nr * PIt;            // poles in the tile (<= 32)
     const int TL = K * PIt;
-    double* xsT = reinterpret_cast<double*>(smraw);                                  // 32 * XS
-    long long* caddr = reinterpret_cast<long long*>(smraw + (size_t)32 * XS * 8);    // NQ * nr cell offsets
+    double* xs = reinterpret_cast<double*>(smraw);                                  // NP * 32
+    long long* caddr = reinterpret_cast<long long*>(smraw + (size_t)NP * 32 * 8);   // NQ * nr cell offsets
     const int caddr_bytes = (NQ * nr * 8 + 15) & ~15;
-    unsigned char* wbase = smraw + (size_t)32 * XS * 8 + caddr_bytes + (size_t)warp * WARP_BYTES;
+    unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + caddr_bytes + (size_t)warp * WARP_BYTES;
     unsigned char* ring = wbase;
-    double* scratch = reinterpret_cast<double*>(wbase + NBUF * REC);
+    double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * CHB);
 
-    // this warp's records [b0, b1) and first row tile
+    // this warp's records [b0, b1) and first block-row q
     const int gpart = t.part * nwarp + warp;
-    const int b0 = partRec[gpart], b1 = partRec[gpart + 1];
-    int rt = partRow[gpart];
+    const int b0 = partBlk[gpart], b1 = partBlk[gpart + 1];
+    int q = partRow[gpart];
+    const int c_first = b0 / LONG_CH, c_last = b1 > b0 ? (b1 - 1) / LONG_CH : c_first - 1;
 
-    auto issue_rec = [&](int b) {
-        if (b < b1) {
-            const unsigned char* src = recs + (size_t)b * REC;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (b % NBUF) * REC);
-            for (int g = lane; g < REC / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
+    auto issue_chunk = [&](int c) {
+        if (c <= c_last) {
+            const unsigned char* src = recs + (size_t)c * CHB;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (c % LONG_NBUF) * CHB);
+            for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
         }
         cp_async_commit();
     };
@@ -627,14 +614,12 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     for (int tt = tid; tt < TL; tt += nth) {
         const int a = tt % na, rest = tt / na;
         const int m = rest % K, bl = rest / K;
-        tab_p[tt] = (short)(a + na * bl);
-        tab_m[tt] = (short)m;
+        tab_row[tt] = (short)(m * 32 + a + na * bl);
         tab_g[tt] = t.ebase + a + A * m + K * A * bl;
     }
-    // unused pole columns of the x tile must be finite (they are multiplied, never stored)
-    for (int i = tid; i < 32 * XS; i += nth) xsT[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NBUF - 1; ++i) issue_rec(b0 + i);
+    issue_chunk(c_first);
+    issue_chunk(c_first + 1);
+    issue_chunk(c_first + 2);
     __syncthreads();
     const int S = sS;
     const int ncell = NQ * nr;
@@ -644,75 +629,65 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
     }
     __syncthreads();
 
-    // ---- stage the x tile in (asynchronous 8-byte copies into xsT[pole][row])
+    // ---- stage the x tile in (asynchronous 8-byte copies, transposed to xs[row][pole])
     for (int c = warp; c < ncell; c += nwarp) {
         const int qq = c / nr, r = c - qq * nr;
         const double* src = X + caddr[c];
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(xsT + (size_t)(r * PIt) * XS + qq * K);
-        for (int tt = lane; tt < TL; tt += 32) cp_async8(dst + (tab_p[tt] * XS + tab_m[tt]) * 8, src + tab_g[tt]);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + (size_t)qq * K * 32 + r * PIt);
+        for (int tt = lane; tt < TL; tt += 32) cp_async8(dst + tab_row[tt] * 8, src + tab_g[tt]);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
 
-    // ---- stream this warp's tile records through the tensor pipe
-    const int lr = lane >> 2, lc = lane & 3;          // fragment row / col of this lane
-    double acc[MB][4][2];
+    // ---- stream this warp's block records
+    const bool active = lane < PT;
+    double acc[K];
 #pragma unroll
-    for (int mb = 0; mb < MB; ++mb)
+    for (int m = 0; m < K; ++m) acc[m] = 0.0;
+    for (int c = c_first; c <= c_last; ++c) {
+        issue_chunk(c + 3);
+        cp_async_wait<3>();            // chunk c has landed (this thread's copies) ...
+        __syncwarp();                  // ... and every lane's
+        const unsigned char* buf = ring + (c % LONG_NBUF) * CHB;
+        const int lo = max(b0, c * LONG_CH) - c * LONG_CH, hi = min(b1, (c + 1) * LONG_CH) - c * LONG_CH;
+        for (int i = lo; i < hi; ++i) {
+            const unsigned char* rec = buf + i * REC;
+            const int2 meta = *reinterpret_cast<const int2*>(rec + KK * 8);
+            const double* hv = reinterpret_cast<const double*>(rec);
+            const double* xv = xs + (size_t)meta.x * K * 32 + lane;
+            double xr[K];
 #pragma unroll
-        for (int nbk = 0; nbk < 4; ++nbk) acc[mb][nbk][0] = acc[mb][nbk][1] = 0.0;
-    for (int b = b0; b < b1; ++b) {
-        issue_rec(b + NBUF - 1);
-        cp_async_wait<NBUF - 1>();         // record b has landed (this thread's copies) ...
-        __syncwarp();                      // ... and every lane's
-        const unsigned char* rec = ring + (b % NBUF) * REC;
-        const int2 meta = *reinterpret_cast<const int2*>(rec + TR * TCc * 8);
-        const double* afr = reinterpret_cast<const double*>(rec) + lane;
-        const double* xcol = xsT + (size_t)lr * XS + meta.x * TCc + lc;     // B[k = lc][n = lr] of pole block 0
+            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[mi * 32];
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            double bf[4];
+            for (int mo = 0; mo < K; ++mo)
 #pragma unroll
-            for (int nbk = 0; nbk < 4; ++nbk) bf[nbk] = xcol[(size_t)(nbk * 8) * XS + kb * 4];
+                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(hv[mo * K + mi], xr[mi], acc[mo]);
+            if (meta.y & 1) {          // end of block-row q: coalesced write through the scratch
+                __syncwarp();
+                if (active) {
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-                const double a = afr[(mb * KB + kb) * 32];
-#pragma unroll
-                for (int nbk = 0; nbk < 4; ++nbk) dmma_m8n8k4(acc[mb][nbk][0], acc[mb][nbk][1], a, bf[nbk]);
-            }
-        }
-        if (meta.y & 1) {              // end of row tile rt: scratch[row][pole], then coalesced writes
-            __syncwarp();
-#pragma unroll
-            for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-                for (int nbk = 0; nbk < 4; ++nbk)
-                    *reinterpret_cast<double2*>(scratch + (mb * 8 + lr) * 32 + nbk * 8 + 2 * lc) =
-                        make_double2(acc[mb][nbk][0], acc[mb][nbk][1]);
-            __syncwarp();
-            for (int cc = 0; cc < CPT; ++cc) {
-                const int q = rt * CPT + cc;
+                    for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
+                }
+                __syncwarp();
                 for (int r = 0; r < nr; ++r) {
                     double* dstg = Y + caddr[q * nr + r];
-                    const double* sc = scratch + cc * K * 32 + r * PIt;
+                    const double* sc = scratch + r * PIt;
                     if (beta == 0.0) {
-                        for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_m[tt] * 32 + tab_p[tt]];
+                        for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
                     } else {
                         for (int tt = lane; tt < TL; tt += 32) {
                             const int g = tab_g[tt];
-                            dstg[g] = fma(alpha, sc[tab_m[tt] * 32 + tab_p[tt]], beta * dstg[g]);
+                            dstg[g] = fma(alpha, sc[tab_row[tt]], beta * dstg[g]);
                         }
                     }
                 }
+                ++q;
+#pragma unroll
+                for (int m = 0; m < K; ++m) acc[m] = 0.0;
             }
-            ++rt;
-#pragma unroll
-            for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-                for (int nbk = 0; nbk < 4; ++nbk) acc[mb][nbk][0] = acc[mb][nbk][1] = 0.0;
         }
-        __syncwarp();                  // the ring slot is refilled by the next iteration's issue
+        __syncwarp();                  // the chunk buffer is refilled by the next iteration's issue
     }
     cp_async_wait<0>();
 }

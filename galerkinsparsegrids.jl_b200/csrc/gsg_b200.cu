@@ -87,7 +87,7 @@ constexpr size_t SMEM_OPTIN_MAX = 227 * 1024;
 constexpr int SHORT_TILE_DOUBLES = 4096;
 constexpr int TMA_STAGE_TARGET_DOUBLES = 5840;
 
-enum class Kind { SHORT_TMA, SHORT, LONG, GENERIC };
+enum class Kind { SHORT_TMA, SHORT, LONG, LONG2, CONSTH, GENERIC };
 
 struct SweepClass {          // one launch of a sweep
     int p = 0;               // pole length class (SHORT_TMA: the largest short class it holds)
@@ -95,6 +95,8 @@ struct SweepClass {          // one launch of a sweep
     int NPOLE = 0, Amin = 0; // generic kernel parameters
     int nwarps = 8;          // long kernel: warps per CTA
     int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
+    int cpl = 1;             // register-tiled long kernel: poles per lane
+    DevBuf<TileL2> l2tiles;
     DevBuf<int> partBlk, partRow;
     size_t smem = 0;
     DevBuf<TileDev> tiles;
@@ -108,6 +110,8 @@ struct SweepClass {          // one launch of a sweep
 struct Direction {
     int A = 1;               // K^(d-1)
     DevBuf<GroupDev> groups;
+    DevBuf<CellOfs> celltab;     // register-tiled long kernel: per group, one entry per 1-D cell
+    DevBuf<int> offtab;          // in-cell offset of pole j: a + K*A*b
     std::vector<SweepClass> classes;
 };
 
@@ -132,6 +136,8 @@ struct gsg_plan {
     // long kernel: per p, the principal sub-block as a compact stream of block records
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
     std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
+    // constant-bank kernel: per p, the pattern blocks' values in pattern order (empty = not usable)
+    std::vector<std::vector<double>> consth_vals;
 
     std::vector<Direction> dirs;
 
@@ -263,6 +269,34 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         }
     }
 
+    // constant-bank kernel (k = 3, N' = 48 and 96): the stored blocks must lie inside the structural
+    // pattern the kernel was unrolled for; otherwise that class falls back to the register-tiled kernel
+    P.consth_vals.assign(n + 1, {});
+    if (K == 3 && !getenv("GSG_NO_CONSTH")) {
+        // N' = 96 is unrolled too (134 KB of code) but measured slower than the register-tiled kernel:
+        // warps of different CTAs run out of phase and thrash the instruction cache (ncu: no_instruction
+        // 4.6 stalls per issue).  Opt-in for experiments only.
+        const int pmax_consth = getenv("GSG_CONSTH5") ? 5 : 4;
+        for (int p = 4; p <= pmax_consth && p <= n; ++p) {
+            const int nq = 1 << p;
+            bool inside = true;
+            std::vector<double> vals;
+            for (int q = 0; q < nq && inside; ++q)
+                for (int qc = 0; qc < nq; ++qc) {
+                    const bool st = blk[(size_t)q * NQ + qc] != 0;
+                    if (pat::touch(q, qc)) {
+                        for (int mo = 0; mo < K; ++mo)
+                            for (int mi = 0; mi < K; ++mi)
+                                vals.push_back(Hd[(size_t)(q * K + mo) * N1 + (qc * K + mi)]);
+                    } else if (st) {
+                        inside = false;
+                        break;
+                    }
+                }
+            if (inside && (int)vals.size() == pat::nblocks(nq) * K * K) P.consth_vals[p] = std::move(vals);
+        }
+    }
+
     // dense principal sub-blocks for the register-resident short classes
     P.dense.resize(n + 1);
     std::vector<double> all;
@@ -366,6 +400,13 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     }
     const bool tma_active = !dir.classes.empty();
 
+    std::vector<CellOfs> celltab;                      // filled by the register-tiled long classes
+    {
+        std::vector<int> offtab(PI);
+        for (int j = 0; j < PI; ++j) offtab[j] = (j % dir.A) + K * dir.A * (j / dir.A);
+        GSG_TRY(dir.offtab.upload(offtab));
+    }
+
     for (int p = 0; p <= n; ++p) {
         SweepClass c;
         c.p = p;
@@ -384,6 +425,128 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             c.kind = Kind::LONG;
         } else {
             c.kind = Kind::GENERIC;
+        }
+        if (c.kind == Kind::LONG && K == 3 && (p == 4 || p == 5) && !P.consth_vals[p].empty()) {
+            // constant-bank kernel: one warp per 32 consecutive (flattened) poles of one group
+            std::vector<TileL2> tl2;
+            for (size_t gi = 0; gi < groups.size(); ++gi) {
+                if (groups[gi].p != p) continue;
+                const GroupDev& g = groups[gi];
+                const long long np = (long long)g.nitems * PI;
+                if (np > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many poles in a pole group");
+                const int ctab = (int)celltab.size();
+                for (int q = 0; q < NQ; ++q) {
+                    const int ld = q == 0 ? 0 : 32 - __builtin_clz((unsigned)q);
+                    const int cd = q == 0 ? 0 : q - (1 << (ld - 1));
+                    const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+                    const long long KS = (long long)KDp * g.S;
+                    celltab.push_back(CellOfs{g.base[ld] + KS * cd, KS * Cd});
+                }
+                for (long long p0 = 0; p0 < np; p0 += 32) {
+                    TileL2 t;
+                    t.ctab = ctab;
+                    t.S = g.S;
+                    t.item0 = (int)(p0 / PI);
+                    t.j0 = (int)(p0 % PI);
+                    t.lo0 = t.item0 % g.S;
+                    t.hi0 = t.item0 / g.S;
+                    t.npoles = (int)std::min<long long>(32, np - p0);
+                    t.part = 0;
+                    tl2.push_back(t);
+                }
+            }
+            if (tl2.empty()) continue;
+            c.kind = Kind::CONSTH;
+            c.ntiles = (int)tl2.size();
+            c.smem = (size_t)CONSTH_WARPS * ((size_t)NP * 32 * 8 + (size_t)NQ * sizeof(CellOfs));
+            GSG_TRY(c.l2tiles.upload(tl2));
+            dir.classes.push_back(std::move(c));
+            continue;
+        }
+        if (c.kind == Kind::LONG && !getenv("GSG_LONG_V1")) {
+            // register-tiled long kernel: tiles of 32*C consecutive (flattened) poles of one group
+            long long maxpoles = 0, ngrp = 0;
+            for (size_t gi = 0; gi < groups.size(); ++gi)
+                if (groups[gi].p == p) { maxpoles = std::max(maxpoles, (long long)groups[gi].nitems * PI); ++ngrp; }
+            if (ngrp == 0) continue;
+            int C = K <= 3 ? 4 : 2;
+            if (const char* e = getenv("GSG_LONG_C")) C = atoi(e);
+            while (C > 1 && (size_t)NP * 32 * C * 8 > 100 * 1024) C >>= 1;      // x tile <= ~98 KB
+            while (C > 1 && 32 * (C >> 1) >= maxpoles) C >>= 1;                   // no wider than the groups
+            int nw2 = C >= 4 ? 4 : 8;       // 167 registers per thread at C = 4: small CTAs, several per SM
+            if (const char* e = getenv("GSG_LONG_NW")) nw2 = atoi(e);
+            nw2 = std::max(1, std::min(nw2, 8));
+            const size_t ring_bytes = (size_t)LONG_NBUF * LONG_CH * REC;
+            while (nw2 > 2 && (size_t)NP * 32 * C * 8 + nw2 * ring_bytes + 2048 > SMEM_OPTIN_MAX) nw2 >>= 1;
+            const size_t smem2 = (size_t)NP * 32 * C * 8 + nw2 * ring_bytes;
+            if (smem2 + 2048 <= SMEM_OPTIN_MAX && (C == 1 || C == 2 || C == 4)) {
+                c.kind = Kind::LONG2;
+                c.cpl = C;
+                c.nwarps = nw2;
+                c.smem = smem2;
+                std::vector<TileL2> base;
+                const int PT = 32 * C;
+                for (size_t gi = 0; gi < groups.size(); ++gi) {
+                    if (groups[gi].p != p) continue;
+                    const GroupDev& g = groups[gi];
+                    const long long np = (long long)g.nitems * PI;
+                    if (np > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many poles in a pole group");
+                    // the group's cell table
+                    const int ctab = (int)celltab.size();
+                    for (int q = 0; q < NQ; ++q) {
+                        const int ld = q == 0 ? 0 : 32 - __builtin_clz((unsigned)q);
+                        const int cd = q == 0 ? 0 : q - (1 << (ld - 1));
+                        const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+                        const long long KS = (long long)KDp * g.S;
+                        celltab.push_back(CellOfs{g.base[ld] + KS * cd, KS * Cd});
+                    }
+                    for (long long p0 = 0; p0 < np; p0 += PT) {
+                        TileL2 t;
+                        t.ctab = ctab;
+                        t.S = g.S;
+                        t.item0 = (int)(p0 / PI);
+                        t.j0 = (int)(p0 % PI);
+                        t.lo0 = t.item0 % g.S;
+                        t.hi0 = t.item0 / g.S;
+                        t.npoles = (int)std::min<long long>(PT, np - p0);
+                        t.part = 0;
+                        base.push_back(t);
+                    }
+                }
+                // row parts: enough CTAs to fill the GPU, at least two block-rows per warp
+                const std::vector<int>& rs = P.lrow_start[p];
+                const int nrec = rs[NQ];
+                // row parts: the x tile is staged once per part, so as few parts as keep one CTA's record
+                // stream short enough to finish well inside the sweep (the long classes run beside the
+                // streaming kernel; their SM time, not their latency, is what counts)
+                int rsplit = (nrec + 1399) / 1400;
+                if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
+                rsplit = std::max(1, std::min(rsplit, std::max(1, NQ / (2 * nw2))));
+                c.rsplit = rsplit;
+                const int G = rsplit * nw2;
+                std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
+                pb[0] = 0; pr[0] = 0;
+                {
+                    const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
+                    int q = 0;
+                    for (int g = 1; g < G; ++g) {
+                        const long long target = total * g / G;
+                        while (q < NQ && (long long)rs[q] + q < target) ++q;
+                        pr[g] = std::max(q, pr[g - 1]);
+                        pb[g] = rs[pr[g]];
+                    }
+                }
+                GSG_TRY(c.partBlk.upload(pb));
+                GSG_TRY(c.partRow.upload(pr));
+                std::vector<TileL2> full;
+                full.reserve(base.size() * rsplit);
+                for (int part = 0; part < rsplit; ++part)
+                    for (TileL2 t1 : base) { t1.part = part; full.push_back(t1); }
+                c.ntiles = (int)full.size();
+                GSG_TRY(c.l2tiles.upload(full));
+                dir.classes.push_back(std::move(c));
+                continue;
+            }
         }
         if (c.kind == Kind::LONG) {
             std::vector<TileLong> ll;
@@ -492,6 +655,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         GSG_TRY(c.tiles.upload(tl));
         dir.classes.push_back(std::move(c));
     }
+    GSG_TRY(dir.celltab.upload(celltab));
     // launch order: the persistent streaming kernel goes on the main stream (index 0); the long
     // classes follow, longest poles first, each on its own forked stream
     std::stable_sort(dir.classes.begin(), dir.classes.end(), [](const SweepClass& a, const SweepClass& b) {
@@ -610,6 +774,65 @@ int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swe
     return fail(GSG_ERR_UNSUPPORTED, "internal: long kernel not instantiated");
 }
 
+template <int K, int C>
+int launch_long2_kc(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                    double* y, double alpha, double beta) {
+    auto kern = sweep_long2_kernel<K, C>;
+    static thread_local size_t configured = 0;
+    GSG_TRY(ensure_smem(kern, c.smem, configured));
+    int tb, tn;
+    tile_range(pl, c.ntiles, tb, tn);
+    if (tn == 0) return 0;
+    const int PI = (int)pl.S.kD / K;
+    kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.offtab.p,
+                                             c.l2tiles.p + tb, pl.lrec[c.p]->p, c.partBlk.p, c.partRow.p, c.p,
+                                             (int)pl.S.kDp, dir.A, PI, pl.dbg);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_check("sweep_long2", K, c);
+}
+
+template <int K>
+int launch_long2_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                   double* y, double alpha, double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        switch (c.cpl) {
+            case 1: return launch_long2_kc<K, 1>(pl, st, dir, c, x, y, alpha, beta);
+            case 2: return launch_long2_kc<K, 2>(pl, st, dir, c, x, y, alpha, beta);
+            case 4: if constexpr (K <= 3) return launch_long2_kc<K, 4>(pl, st, dir, c, x, y, alpha, beta); break;
+        }
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: register-tiled long kernel not instantiated");
+}
+
+template <int K, int PP>
+int launch_consth_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                     double* y, double alpha, double beta) {
+    auto kern = sweep_consth_kernel<K, PP>;
+    static thread_local size_t configured = 0;
+    GSG_TRY(ensure_smem(kern, c.smem, configured));
+    int tb, tn;
+    tile_range(pl, c.ntiles, tb, tn);
+    if (tn == 0) return 0;
+    static_assert(sizeof(HBlocks<K, PP>) + 128 < 32764, "pattern blocks must fit the kernel parameter space");
+    HBlocks<K, PP> hb;
+    const std::vector<double>& vals = pl.consth_vals[PP];
+    if (vals.size() * sizeof(double) != sizeof(hb.v)) return fail(GSG_ERR_UNSUPPORTED, "internal: pattern block table size mismatch");
+    std::memcpy(hb.v, vals.data(), sizeof(hb.v));
+    const int PI = (int)pl.S.kD / K;
+    const int grid = (tn + CONSTH_WARPS - 1) / CONSTH_WARPS;
+    kern<<<grid, 32 * CONSTH_WARPS, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.offtab.p,
+                                                   c.l2tiles.p + tb, tn, (int)pl.S.kDp, dir.A, PI, hb);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_check("sweep_consth", K, c);
+}
+
+int launch_consth(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                  double* y, double alpha, double beta) {
+    if (pl.S.k == 3 && c.p == 4) return launch_consth_kp<3, 4>(pl, st, dir, c, x, y, alpha, beta);
+    if (pl.S.k == 3 && c.p == 5) return launch_consth_kp<3, 5>(pl, st, dir, c, x, y, alpha, beta);
+    return fail(GSG_ERR_UNSUPPORTED, "internal: constant-bank kernel not instantiated");
+}
+
 template <int K>
 int launch_generic_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                      double* y, double alpha, double beta) {
@@ -643,6 +866,8 @@ int launch_class(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swee
         case Kind::SHORT_TMA: GSG_K_SWITCH(launch_short_tma, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::SHORT: GSG_K_SWITCH(launch_short_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::LONG: GSG_K_SWITCH(launch_long_k, pl, st, dir, c, x, y, alpha, beta); break;
+        case Kind::LONG2: GSG_K_SWITCH(launch_long2_k, pl, st, dir, c, x, y, alpha, beta); break;
+        case Kind::CONSTH: return launch_consth(pl, st, dir, c, x, y, alpha, beta);
         case Kind::GENERIC:
             GSG_K_SWITCH(launch_generic_k, pl, st, dir, c, x, y, alpha, beta);
             return launch_generic_k<0>(pl, st, dir, c, x, y, alpha, beta);
@@ -877,10 +1102,12 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     GSG_CUDA(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
     P->stream = P->own_stream;
     GSG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    int prio_lo = 0, prio_hi = 0;     // long-pole CTAs first: they run beside the persistent streaming kernel
+    GSG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     P->aux.assign(n + 3, nullptr);
     P->ev_done.assign(n + 3, nullptr);
     for (int i = 0; i < n + 3; ++i) {
-        GSG_CUDA(cudaStreamCreateWithFlags(&P->aux[i], cudaStreamNonBlocking));
+        GSG_CUDA(cudaStreamCreateWithPriority(&P->aux[i], cudaStreamNonBlocking, prio_hi));
         GSG_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
     }
     GSG_TRY(P->tile_counter.resize(4));
@@ -1019,6 +1246,7 @@ int gsg_debug_stamps(gsg_plan* plan, long long* out, int n) {
     GSG_TRY(check_plan(plan));
     if (!plan->dbg) {
         GSG_TRY(plan->dbgbuf.resize(64 * 8));
+        cudaMemset(plan->dbgbuf.p, 0, 64 * 8 * sizeof(long long));
         plan->dbg = plan->dbgbuf.p;
         return 0;
     }

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 namespace gsgk {
 
@@ -690,6 +691,412 @@ sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double a
         __syncwarp();                  // the chunk buffer is refilled by the next iteration's issue
     }
     cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// Long poles, register-tiled (the shipped path for N' > 32): lanes = poles, C poles per lane.
+// A CTA tile holds PT = 32*C consecutive poles of one pole group (flattened pole index
+// item * PI + j, so a tile may straddle items) and one ROW PART of the principal sub-block; the
+// whole x tile sits in shared memory as xs[row][PT] (conflict-free for lanes = poles).  Every
+// warp owns a contiguous range of whole block-rows and streams its K x K block records through
+// a private cp.async ring (same record stream as sweep_long_kernel).  Per record a lane loads
+// the K*K uniform H values once (broadcast LDS) and K*C of its own x values and issues K*K*C
+// DFMAs: shared-memory wavefronts per DFMA fall from 2.9 (C = 1) to 1.2 (C = 4) -- shared-memory
+// delivery, not the fp64 pipe, is what bounds this kernel.
+// Global traffic needs no tables or scratch: with pole = c*32 + lane every warp-level access of a
+// fixed (cell, mode, c) touches 32 consecutive poles, i.e. one contiguous (A > 1) or stride-K
+// (A = 1, the other modes fill the gaps) run.  For y += alpha*D x the old y of the NEXT block-row
+// is prefetched into registers before that row's records are processed, so the read-modify-write
+// latency is hidden behind the row's arithmetic.
+//   element (q, mo, pole): base[level(q)] + KS*(c(q) + C(q)*hi) + KDp*lo + a + K*A*b + A*mo,
+//   pole -> item r = pole / PI (lo = r % S, hi = r / S), j = pole % PI (a = j % A, b = j / A).
+// ------------------------------------------------------------------------------------------
+struct TileL2 {
+    int ctab;      // offset of the group's cell table (one CellOfs per 1-D cell q)
+    int S;         // prod of cells of dims < d
+    int item0;     // first item of the tile and ...
+    int j0;        // ... first pole inside it (flattened pole = item * PI + j)
+    int lo0, hi0;  // item0 = lo0 + S * hi0
+    int npoles;    // <= 32*C
+    int part;      // row part of the matrix this CTA computes
+};
+
+struct CellOfs {   // multi-cell of 1-D cell q for item (lo, hi): bq + KDp*lo + kc*hi
+    long long bq;  // base[level(q)] + KDp*S*c(q)
+    long long kc;  // KDp*S*C(level(q))
+};
+
+__device__ __forceinline__ void cp_async8_zfill(unsigned dst, const void* src, bool valid) {
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+template <int K, int C>
+struct LongOperands {          // one block record's operands, register-resident
+    double h[K * K];
+    double x[K][C];
+    int flags;
+};
+
+// shared-memory loads with explicit 32-bit addresses: keeps the record loop's address arithmetic
+// in registers (the compiler otherwise rematerialises the smem bases from SR_TID every record)
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double d;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(d) : "r"(addr));
+    return d;
+}
+__device__ __forceinline__ void lds_v2f64(double& a, double& b, unsigned addr) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ int2 lds_v2s32(unsigned addr) {
+    int2 r;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+template <int K, int C>
+__global__ void __launch_bounds__(256)
+sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+                   const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
+                   const TileL2* __restrict__ tiles, const unsigned char* __restrict__ recs,
+                   const int* __restrict__ partBlk, const int* __restrict__ partRow, int p, int KDp, int A, int PI,
+                   long long* __restrict__ dbg) {     // dbg: optional per-warp clock stamps (first 8 CTAs)
+    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
+    constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
+    constexpr int RINGREC = LONG_CH * LONG_NBUF;              // records the ring holds
+    constexpr int PT = 32 * C;
+    const long long t_start = clock64();
+    const int NQ = 1 << p, NP = K * NQ;
+    extern __shared__ __align__(128) unsigned char smraw[];
+
+    const TileL2 t = tiles[blockIdx.x];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int warp = tid >> 5, nwarp = nth >> 5;
+    int lane = tid & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    double* xs = reinterpret_cast<double*>(smraw);                                  // NP * PT
+    unsigned char* ring = smraw + (size_t)NP * PT * 8 + (size_t)warp * (LONG_NBUF * CHB);
+    unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    unsigned xs_s = (unsigned)__cvta_generic_to_shared(xs) + lane * 8;
+    // opaque copies: stops the compiler from rematerialising these bases (S2R + IMADs) per record
+    asm volatile("mov.u32 %0, %0;" : "+r"(ring_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(xs_s));
+    const CellOfs* ctab = celltab + t.ctab;
+
+    // this warp's records [b0, b1) and first block-row q
+    const int gpart = t.part * nwarp + warp;
+    const int b0 = partBlk[gpart], b1 = partBlk[gpart + 1];
+    int q = partRow[gpart];
+    const int c_first = b0 / LONG_CH, c_last = b1 > b0 ? (b1 - 1) / LONG_CH : c_first - 1;
+
+    auto issue_chunk = [&](int c) {
+        if (c <= c_last) {
+            const unsigned char* src = recs + (size_t)c * CHB;
+            const unsigned dst = ring_s + (c % LONG_NBUF) * CHB;
+            for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
+        }
+        cp_async_commit();
+    };
+    issue_chunk(c_first);
+    issue_chunk(c_first + 1);
+    issue_chunk(c_first + 2);
+
+    // per-lane pole constants (no integer divisions: the tile carries its first item / pole)
+    long long u[C], v[C];
+    bool ok[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int pl = c * 32 + lane;
+        ok[c] = pl < t.npoles;
+        int jj = t.j0 + (ok[c] ? pl : 0), lo = t.lo0, hi = t.hi0;
+        while (jj >= PI) {
+            jj -= PI;
+            if (++lo == t.S) { lo = 0; ++hi; }
+        }
+        u[c] = (long long)KDp * lo + offtab[jj];
+        v[c] = hi;
+    }
+
+    // ---- stage the x tile in (asynchronous 8-byte copies, coalesced per (cell, mode, c))
+    for (int qq = warp; qq < NQ; qq += nwarp) {
+        const CellOfs co = ctab[qq];
+        const unsigned dst = xs_s + qq * (K * PT * 8);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const double* src = X + co.bq + u[c] + co.kc * v[c];
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo) cp_async8_zfill(dst + (mo * PT + c * 32) * 8, src + A * mo, ok[c]);
+        }
+    }
+    cp_async_commit();
+    const long long t_issued = clock64();
+    cp_async_wait<0>();
+    __syncthreads();
+    const long long t_staged = clock64();
+    if (b1 <= b0) return;
+
+    // ---- stream this warp's block records, software-pipelined one record ahead (two register
+    //      sets used alternately)
+    double acc[K][C], yold[K][C];
+#pragma unroll
+    for (int m = 0; m < K; ++m)
+#pragma unroll
+        for (int c = 0; c < C; ++c) { acc[m][c] = 0.0; yold[m][c] = 0.0; }
+
+    long long rowofs[C];
+    auto row_begin = [&](int qr) {      // element offsets of block-row qr; prefetch its old y
+        const CellOfs co = ctab[qr];
+#pragma unroll
+        for (int c = 0; c < C; ++c) rowofs[c] = co.bq + u[c] + co.kc * v[c];
+        if (accumulate) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int mo = 0; mo < K; ++mo)
+                    if (ok[c]) yold[mo][c] = Y[rowofs[c] + A * mo];
+        }
+    };
+    auto fetch = [&](int i, LongOperands<K, C>& o) {
+        if ((i & (LONG_CH - 1)) == 0 || i == b0) {
+            // entering chunk ci: every lane has finished reading chunk ci-1 (its last record is in
+            // registers), so that buffer is refilled with chunk ci+3; then chunk ci must have landed
+            __syncwarp();
+            issue_chunk(i / LONG_CH + 3);
+            cp_async_wait<3>();
+            __syncwarp();
+        }
+        const unsigned ra = ring_s + (i & (RINGREC - 1)) * REC;
+        if constexpr ((KK & 1) == 1) {
+#pragma unroll
+            for (int e = 0; e + 1 < KK; e += 2) lds_v2f64(o.h[e], o.h[e + 1], ra + e * 8);
+            o.h[KK - 1] = lds_f64(ra + (KK - 1) * 8);
+        } else {
+#pragma unroll
+            for (int e = 0; e < KK; e += 2) lds_v2f64(o.h[e], o.h[e + 1], ra + e * 8);
+        }
+        const int2 meta = lds_v2s32(ra + KK * 8);
+        o.flags = meta.y;
+        const unsigned xa = xs_s + meta.x * (K * PT * 8);
+#pragma unroll
+        for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) o.x[mi][cc] = lds_f64(xa + (mi * PT + cc * 32) * 8);
+    };
+    auto compute = [&](const LongOperands<K, C>& o) {
+#pragma unroll
+        for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) acc[mo][cc] = fma(o.h[mo * K + mi], o.x[mi][cc], acc[mo][cc]);
+    };
+    auto row_end = [&](bool more) {
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo) {
+                if (ok[cc])
+                    Y[rowofs[cc] + A * mo] = accumulate ? fma(alpha, acc[mo][cc], yold[mo][cc]) : alpha * acc[mo][cc];
+                acc[mo][cc] = 0.0;
+            }
+        ++q;
+        if (more) row_begin(q);
+    };
+
+    row_begin(q);
+    LongOperands<K, C> ra_, rb_;
+    fetch(b0, ra_);
+    for (int i = b0;;) {
+        if (i + 1 < b1) fetch(i + 1, rb_);
+        compute(ra_);
+        if (ra_.flags & 1) row_end(i + 1 < b1);
+        if (++i >= b1) break;
+        if (i + 1 < b1) fetch(i + 1, ra_);
+        compute(rb_);
+        if (rb_.flags & 1) row_end(i + 1 < b1);
+        if (++i >= b1) break;
+    }
+    cp_async_wait<0>();
+    if (dbg && blockIdx.x < 8 && lane == 0) {
+        long long* o = dbg + (blockIdx.x * 8 + warp) * 8;
+        o[0] = t_start; o[1] = t_issued; o[2] = t_staged; o[3] = clock64(); o[4] = b1 - b0; o[5] = q - partRow[gpart];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Medium poles (N' = 48, 96 at k = 3), matrix in the constant bank.  The block pattern of the 1-D
+// operator is structural -- block (q, r) is stored iff the closed supports of the two hierarchical
+// cells intersect or touch periodically (checked against the host's H at
+// plan creation) -- so the whole principal sub-block is unrolled at compile time and every DFMA
+// takes its H operand as an immediate constant-bank address of a __grid_constant__ parameter:
+// the matrix costs no shared-memory bandwidth at all (the register-tiled kernel above is bound by
+// exactly that).  One warp = 32 consecutive poles (lanes = poles); warps are independent (no CTA
+// barrier): each stages its own x tile xs[row][32] with asynchronous copies, then walks the rows
+// with 3 conflict-free LDS.64 + 9 DFMA per block; old y is prefetched two block-rows ahead.
+// ------------------------------------------------------------------------------------------
+namespace pat {
+constexpr int FULL = 1 << 16;
+__host__ __device__ constexpr int cell_lo(int q) {
+    if (q == 0) return 0;
+    int l = 0;
+    for (int t = q; t; t >>= 1) ++l;
+    return (q - (1 << (l - 1))) * (FULL >> (l - 1));
+}
+__host__ __device__ constexpr int cell_hi(int q) {
+    if (q == 0) return FULL;
+    int l = 0;
+    for (int t = q; t; t >>= 1) ++l;
+    return (q - (1 << (l - 1)) + 1) * (FULL >> (l - 1));
+}
+__host__ __device__ constexpr bool touch(int q, int r) {
+    const int a1 = cell_lo(q), b1 = cell_hi(q), a2 = cell_lo(r), b2 = cell_hi(r);
+    return (a1 <= b2 && a2 <= b1) || (b1 == FULL && a2 == 0) || (b2 == FULL && a1 == 0);
+}
+// number of pattern blocks before (q, r) in row-major order, rows/cols < nq
+__host__ __device__ constexpr int block_index(int nq, int q, int r) {
+    int n = 0;
+    for (int i = 0; i < q; ++i)
+        for (int j = 0; j < nq; ++j) n += touch(i, j) ? 1 : 0;
+    for (int j = 0; j < r; ++j) n += touch(q, j) ? 1 : 0;
+    return n;
+}
+__host__ __device__ constexpr int nblocks(int nq) { return block_index(nq, nq, 0); }
+}  // namespace pat
+
+template <int K, int P>
+struct HBlocks {
+    double v[pat::nblocks(1 << P) * K * K];
+};
+
+template <int K, int P, int Q, int R>
+__device__ __forceinline__ void consth_block(const HBlocks<K, P>& hb, unsigned xs_s, double (&acc)[2][K]) {
+    if constexpr (pat::touch(Q, R)) {
+        constexpr int BI = pat::block_index(1 << P, Q, R);
+        constexpr int OFF = BI * K * K;
+        constexpr int SET = BI & 1;
+        double x[K];
+#pragma unroll
+        for (int mi = 0; mi < K; ++mi) x[mi] = lds_f64(xs_s + (R * K + mi) * 256);
+#pragma unroll
+        for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo) acc[SET][mo] = fma(hb.v[OFF + mo * K + mi], x[mi], acc[SET][mo]);
+    }
+}
+
+template <int K, int P, int Q, int... Rs>
+__device__ __forceinline__ void consth_row(const HBlocks<K, P>& hb, unsigned xs_s, double (&acc)[2][K],
+                                           std::integer_sequence<int, Rs...>) {
+    (consth_block<K, P, Q, Rs>(hb, xs_s, acc), ...);
+}
+
+template <int K, int P>
+struct ConstHCtx {
+    const double* X;
+    double* Y;
+    const CellOfs* ctab_s;     // the group's cell table, in shared memory
+    long long u, v;
+    double alpha;
+    int A;
+    bool ok, accumulate;
+    unsigned xs_s;
+};
+
+template <int K, int P, int Q>
+__device__ __forceinline__ void consth_rows(const HBlocks<K, P>& hb, const ConstHCtx<K, P>& cx,
+                                            long long (&rowofs)[3], double (&yold)[3][K]) {
+    constexpr int NQ = 1 << P;
+    if constexpr (Q < NQ) {
+        // prefetch old y of block-row Q + 2 (slots rotate modulo 3)
+        if constexpr (Q + 2 < NQ) {
+            const CellOfs co = cx.ctab_s[Q + 2];
+            rowofs[(Q + 2) % 3] = co.bq + cx.u + co.kc * cx.v;
+            if (cx.accumulate && cx.ok) {
+#pragma unroll
+                for (int mo = 0; mo < K; ++mo) yold[(Q + 2) % 3][mo] = cx.Y[rowofs[(Q + 2) % 3] + cx.A * mo];
+            }
+        }
+        double acc[2][K];
+#pragma unroll
+        for (int mo = 0; mo < K; ++mo) acc[0][mo] = acc[1][mo] = 0.0;
+        consth_row<K, P, Q>(hb, cx.xs_s, acc, std::make_integer_sequence<int, NQ>{});
+        if (cx.ok) {
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo) {
+                const double r = acc[0][mo] + acc[1][mo];
+                cx.Y[rowofs[Q % 3] + cx.A * mo] = cx.accumulate ? fma(cx.alpha, r, yold[Q % 3][mo]) : cx.alpha * r;
+            }
+        }
+        consth_rows<K, P, Q + 1>(hb, cx, rowofs, yold);
+    }
+}
+
+constexpr int CONSTH_WARPS = 4;
+
+template <int K, int P>
+__global__ void __launch_bounds__(32 * CONSTH_WARPS)
+sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+                    const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
+                    const TileL2* __restrict__ tiles, int ntiles, int KDp, int A, int PI,
+                    const __grid_constant__ HBlocks<K, P> hb) {
+    constexpr int NQ = 1 << P, NP = K * NQ;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    const int ti = blockIdx.x * CONSTH_WARPS + warp;
+    if (ti >= ntiles) return;                       // warps are independent: no CTA-wide barrier below
+    const TileL2 t = tiles[ti];
+    unsigned char* wbase = smraw + (size_t)warp * (NP * 32 * 8 + NQ * sizeof(CellOfs));
+    CellOfs* ctab_s = reinterpret_cast<CellOfs*>(wbase + NP * 32 * 8);
+    unsigned xs_s = (unsigned)__cvta_generic_to_shared(wbase) + lane * 8;
+    asm volatile("mov.u32 %0, %0;" : "+r"(xs_s));
+
+    // per-lane pole constants
+    const bool ok = lane < t.npoles;
+    long long u, v;
+    {
+        int jj = t.j0 + (ok ? lane : 0), lo = t.lo0, hi = t.hi0;
+        while (jj >= PI) {
+            jj -= PI;
+            if (++lo == t.S) { lo = 0; ++hi; }
+        }
+        u = (long long)KDp * lo + offtab[jj];
+        v = hi;
+    }
+    // stage the cell table and the x tile
+    for (int qq = lane; qq < NQ; qq += 32) ctab_s[qq] = celltab[t.ctab + qq];
+    __syncwarp();
+#pragma unroll 4
+    for (int qq = 0; qq < NQ; ++qq) {
+        const CellOfs co = ctab_s[qq];
+        const double* src = X + co.bq + u + co.kc * v;
+#pragma unroll
+        for (int mo = 0; mo < K; ++mo) cp_async8_zfill(xs_s + (qq * K + mo) * 256, src + A * mo, ok);
+    }
+    cp_async_commit();
+
+    ConstHCtx<K, P> cx;
+    cx.X = X; cx.Y = Y; cx.ctab_s = ctab_s; cx.u = u; cx.v = v; cx.alpha = alpha; cx.A = A;
+    cx.ok = ok; cx.accumulate = accumulate != 0; cx.xs_s = xs_s;
+    long long rowofs[3];
+    double yold[3][K];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int mo = 0; mo < K; ++mo) yold[i][mo] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 2 && r < NQ; ++r) {          // rows 0 and 1: prefetched here, the rest two rows ahead
+        const CellOfs co = ctab_s[r];
+        rowofs[r] = co.bq + u + co.kc * v;
+        if (cx.accumulate && ok) {
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo) yold[r][mo] = Y[rowofs[r] + A * mo];
+        }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    consth_rows<K, P, 0>(hb, cx, rowofs, yold);
 }
 
 // ------------------------------------------------------------------------------------------

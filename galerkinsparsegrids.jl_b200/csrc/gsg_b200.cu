@@ -102,6 +102,8 @@ struct SweepClass {          // one launch of a sweep
     DevBuf<TileDev> tiles;
     DevBuf<TileLong> ltiles;
     DevBuf<TileS> stiles;
+    DevBuf<TileS2> s2tiles;     // second-generation streaming kernel
+    bool stream2 = false;
     ShortParams sprm{};
     int ntiles = 0;
     double short_dofs = 0;   // SHORT_TMA: DOFs this launch processes (for the roofline figure)
@@ -362,8 +364,9 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         c.p = P.short_pmax;
         const int cmin = 1 << P.short_pmax;
         int CT = std::max(cmin, (TMA_STAGE_TARGET_DOUBLES / KDp) / cmin * cmin);   // multi-cells per tile
-        const size_t fixed = 128 + 8 * sizeof(TileS) + (size_t)PI * 4 + 128;
+        const size_t fixed = 128 + std::max(8 * sizeof(TileS), 4 * sizeof(TileS2)) + (size_t)PI * 4 + 128;
         int ns = 4;
+        if (const char* e = getenv("GSG_STREAM_NS")) ns = std::max(2, std::min(4, atoi(e)));
         while (ns > 2 && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) --ns;
         while (CT > cmin && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) CT -= cmin;
         if (fixed + (size_t)ns * CT * KDp * 8 <= SMEM_OPTIN_MAX) {
@@ -386,6 +389,45 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             }
             c.ntiles = (int)tl.size();
             for (const TileS& t : tl) c.short_dofs += (double)(1 << t.P) * t.nr * KD;
+            // second-generation descriptors: ready-made runs of memory-contiguous multi-cells
+            c.stream2 = !getenv("GSG_STREAM_V1") && CT <= TILE2_MAXRUN && ns <= 4;
+            if (c.stream2) {
+                std::vector<TileS2> tl2(tl.size());
+                for (size_t ti = 0; ti < tl.size() && c.stream2; ++ti) {
+                    const TileS& t = tl[ti];
+                    TileS2& o = tl2[ti];
+                    std::memset(&o, 0, sizeof(o));
+                    o.P = t.P;
+                    o.nr = t.nr;
+                    o.ncell = (int)t.nr << t.P;
+                    int nruns = 0;
+                    for (int q = 0; q < (1 << t.P); ++q) {
+                        const int ld = q == 0 ? 0 : 32 - __builtin_clz((unsigned)q);
+                        const int cd = q == 0 ? 0 : q - (1 << (ld - 1));
+                        const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+                        long long prev = -2;
+                        for (int r = 0; r < t.nr; ++r) {
+                            const int item = t.r0 + r, lo = item % t.S, hi = item / t.S;
+                            const long long ofs = t.base[ld] + (long long)KDp * (lo + (long long)t.S * (cd + (long long)Cd * hi));
+                            if (ofs % KDp != 0 || ofs / KDp > 0x7fffffffLL) { c.stream2 = false; break; }
+                            const long long cell = ofs / KDp;
+                            if (cell == prev + 1 && nruns > 0) {
+                                ++o.run[nruns - 1].n;
+                            } else {
+                                if (nruns == TILE2_MAXRUN) { c.stream2 = false; break; }
+                                o.run[nruns].cell0 = (int)cell;
+                                o.run[nruns].scell = (short)(q * t.nr + r);
+                                o.run[nruns].n = 1;
+                                ++nruns;
+                            }
+                            prev = cell;
+                        }
+                        if (!c.stream2) break;
+                    }
+                    o.nruns = nruns;
+                }
+                if (c.stream2) GSG_TRY(c.s2tiles.upload(tl2));
+            }
             if (c.ntiles > 0) {
                 GSG_TRY(c.stiles.upload(tl));
                 c.sprm.KD = KD;
@@ -471,9 +513,14 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             if (ngrp == 0) continue;
             int C = K <= 3 ? 4 : 2;
             if (const char* e = getenv("GSG_LONG_C")) C = atoi(e);
-            while (C > 1 && (size_t)NP * 32 * C * 8 > 100 * 1024) C >>= 1;      // x tile <= ~98 KB
+            // x tile: up to ~98 KB keeps two CTAs per SM; beyond that a CTA owns its SM anyway, so take
+            // the widest tile that fits (shared-memory wavefronts per DFMA fall with C)
+            size_t xcap = 200 * 1024;
+            if (const char* e = getenv("GSG_LONG_XCAP")) xcap = (size_t)atoi(e) * 1024;
+            while (C > 1 && (size_t)NP * 32 * C * 8 > xcap) C >>= 1;
             while (C > 1 && 32 * (C >> 1) >= maxpoles) C >>= 1;                   // no wider than the groups
-            int nw2 = C >= 4 ? 4 : 8;       // 167 registers per thread at C = 4: small CTAs, several per SM
+            // ~190 registers per thread at C = 4: small CTAs (several per SM) while the tile is small
+            int nw2 = (C >= 4 && (size_t)NP * 32 * C * 8 <= 100 * 1024) ? 4 : 8;
             if (const char* e = getenv("GSG_LONG_NW")) nw2 = atoi(e);
             nw2 = std::max(1, std::min(nw2, 8));
             const size_t ring_bytes = (size_t)LONG_NBUF * LONG_CH * REC;
@@ -713,6 +760,13 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < pl.prof_ev.size();
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
+        if (c.stream2) {
+            auto kern2 = sweep_stream_kernel<K>;
+            static thread_local size_t configured2 = 0;
+            GSG_TRY(ensure_smem(kern2, c.smem, configured2));
+            kern2<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, c.s2tiles.p + tb, tn, hd,
+                                                         c.sprm, pl.tile_counter.p, pl.dbg);
+        } else
         kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
                                                                          c.stiles.p + tb, tn, hd, c.sprm,
                                                                          pl.tile_counter.p, pl.dbg);

@@ -430,6 +430,238 @@ sweep_short_tma_kernel(const double* __restrict__ X, double* __restrict__ Y, dou
 }
 
 // ------------------------------------------------------------------------------------------
+// Streaming kernel, second generation (the shipped path): same data flow as above, but the
+// producer is split into a LOADER warp and a STORER warp so that loads, stores and the wait for a
+// store's shared-memory read-out no longer serialise in one instruction stream (measured with the
+// clock stamps: the single producer spent ~5 500 cycles per tile, the compute warps ~2 000).
+//  * tile descriptors carry ready-made runs {first multi-cell, count, position in the stage}:
+//    no address arithmetic (divisions) in the producer, one bulk copy per run;
+//  * the loader claims the NEXT tile (atomic counter) and fetches its descriptor while it waits
+//    for a free stage, so the claim round trip is off the critical path;
+//  * the storer frees a stage one iteration late (cp.async.bulk.wait_group.read 1), so a store's
+//    read-out overlaps the next store's issue.
+// Barriers per stage: full (loader -> compute, tx bytes), done (compute -> storer), empty
+// (storer -> loader).
+// ------------------------------------------------------------------------------------------
+constexpr int TILE2_MAXRUN = 16;
+
+struct TileS2 {                // 144 bytes = 36 words, fetched one word per lane
+    int nruns;
+    int ncell;                 // multi-cells in the tile (= nr << P)
+    short P, nr;
+    int pad;
+    struct Run {
+        int cell0;             // first multi-cell (global index; offset = cell0 * KDp doubles)
+        short scell;           // position in the stage (multi-cell units)
+        short n;               // consecutive multi-cells
+    } run[TILE2_MAXRUN];
+};
+static_assert(sizeof(TileS2) == 144, "TileS2 layout");
+constexpr int TILE2_WORDS = sizeof(TileS2) / 4;
+
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// compute one tile: one pole per thread and item; U items are processed together for ILP
+template <int K, int P, int U>
+__device__ __forceinline__ void short_tile_compute2(double* xs, const HDense<K>& hd, int nr, int KDp, int A, int PI,
+                                                    const int* pole_off, double alpha, int ctid, int ncth) {
+    constexpr int NQ = 1 << P, NP = K * NQ;
+    constexpr int RC = NP < 12 ? NP : 12;        // rows per accumulation chunk
+    constexpr int HO = ShortDims<K>::hoff(P);
+    const size_t qstride = (size_t)nr * KDp;
+    for (int r0 = 0; r0 < nr; r0 += U) {
+        for (int j = ctid; j < PI; j += ncth) {
+            double* pole[U];
+            double x[U][NP];
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+                const int r = r0 + uu < nr ? r0 + uu : nr - 1;     // tail: recompute the last item (idempotent)
+                pole[uu] = xs + (size_t)r * KDp + pole_off[j];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int m = 0; m < K; ++m) x[uu][q * K + m] = pole[uu][q * qstride + A * m];
+            }
+#pragma unroll
+            for (int i0 = 0; i0 < NP; i0 += RC) {
+                double acc[U][RC];
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu)
+#pragma unroll
+                    for (int i = 0; i < RC; ++i) acc[uu][i] = 0.0;
+#pragma unroll
+                for (int jx = 0; jx < NP; ++jx)
+#pragma unroll
+                    for (int i = 0; i < RC; ++i)
+                        if (i0 + i < NP) {
+#pragma unroll
+                            for (int uu = 0; uu < U; ++uu)
+                                acc[uu][i] = fma(hd.v[HO + (i0 + i) * NP + jx], x[uu][jx], acc[uu][i]);
+                        }
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu) {
+                    if (uu > 0 && r0 + uu >= nr) continue;          // tail duplicate: nothing to write
+#pragma unroll
+                    for (int i = 0; i < RC; ++i)
+                        if (i0 + i < NP) {
+                            const int q = (i0 + i) / K, m = (i0 + i) % K;
+                            pole[uu][q * qstride + A * m] = alpha * acc[uu][i];
+                        }
+                }
+            }
+        }
+    }
+}
+
+constexpr int STREAM_COMPUTE_WARPS = 8;
+constexpr int STREAM_THREADS = 32 * (STREAM_COMPUTE_WARPS + 2);
+
+template <int K>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+                    const TileS2* __restrict__ tiles, int ntiles,
+                    const __grid_constant__ HDense<K> hd, const ShortParams prm,
+                    int* __restrict__ counter,       // dynamic tile scheduler (zeroed before the launch)
+                    long long* __restrict__ dbg) {   // dbg: optional per-phase clock stamps (CTA 0)
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);     // full[NS], done[NS], empty[NS]
+    TileS2* sdesc = reinterpret_cast<TileS2*>(smraw + 128);                      // per-stage tile descriptor
+    const int PI = prm.KD / K;
+    int* pole_off = reinterpret_cast<int*>(smraw + 128 + 4 * sizeof(TileS2));
+    size_t off = 128 + 4 * sizeof(TileS2) + (size_t)PI * 4;
+    off = (off + 127) & ~(size_t)127;
+    double* ring = reinterpret_cast<double*>(smraw + off);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NS = prm.nstage;            // <= 4
+    const int KDp = prm.KDp;
+    const unsigned cell_bytes = (unsigned)KDp * 8u;
+
+    for (int j = tid; j < PI; j += blockDim.x) {
+        const int b = j / prm.A, a = j - b * prm.A;
+        pole_off[j] = a + K * prm.A * b;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            tma::mbar_init(tma::smem_u32(&bars[s]), 1);
+            tma::mbar_init(tma::smem_u32(&bars[4 + s]), STREAM_COMPUTE_WARPS);
+            tma::mbar_init(tma::smem_u32(&bars[8 + s]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= loader =================
+        auto claim = [&]() -> int {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(counter, 1);
+            return __shfl_sync(0xffffffffu, idx, 0);
+        };
+        auto fetch = [&](int idx, int& w0, int& w1) {       // descriptor words lane and lane + 32
+            w0 = 0; w1 = 0;
+            if (idx < ntiles) {
+                const int* src = reinterpret_cast<const int*>(tiles + idx);
+                w0 = __ldg(src + lane);
+                if (lane + 32 < TILE2_WORDS) w1 = __ldg(src + lane + 32);
+            }
+        };
+        int idx = claim();
+        int w0, w1;
+        fetch(idx, w0, w1);
+        for (int it = 0;; ++it) {
+            const int s = it % NS;
+            const long long c0 = clock64();
+            if (it >= NS) tma::mbar_wait(tma::smem_u32(&bars[8 + s]), (unsigned)(((it / NS) - 1) & 1));
+            const long long c1 = clock64();
+            int* dw = reinterpret_cast<int*>(&sdesc[s]);
+            const unsigned bar = tma::smem_u32(&bars[s]);
+            if (idx >= ntiles) {
+                if (lane == 0) {
+                    sdesc[s].P = -1;
+                    tma::mbar_arrive(bar);          // release the compute warps without data
+                }
+                break;
+            }
+            dw[lane] = w0;
+            if (lane + 32 < TILE2_WORDS) dw[lane + 32] = w1;
+            __syncwarp();
+            const TileS2& t = sdesc[s];
+            if (lane == 0) tma::mbar_expect_tx(bar, (unsigned)t.ncell * cell_bytes);
+            __syncwarp();
+            if (lane < t.nruns) {
+                const TileS2::Run rn = t.run[lane];
+                tma::bulk_g2s(tma::smem_u32(ring + (size_t)s * prm.stage_doubles + (size_t)rn.scell * KDp),
+                              X + (size_t)rn.cell0 * KDp, (unsigned)rn.n * cell_bytes, bar);
+            }
+            const long long c2 = clock64();
+            idx = claim();                          // next tile: claimed and fetched while this one is in flight
+            fetch(idx, w0, w1);
+            if (dbg && blockIdx.x == 0 && it < 64 && lane == 0) {
+                dbg[it * 8 + 0] = c0; dbg[it * 8 + 1] = c1; dbg[it * 8 + 2] = c2;
+            }
+        }
+    } else if (warp == 1) {
+        // ================= storer =================
+        int it = 0;
+        for (;; ++it) {
+            const int s = it % NS;
+            const long long c0 = clock64();
+            tma::mbar_wait(tma::smem_u32(&bars[4 + s]), (unsigned)((it / NS) & 1));          // tile computed
+            const long long c1 = clock64();
+            const TileS2& t = sdesc[s];
+            if (t.P < 0) break;
+            if (lane < t.nruns) {
+                const TileS2::Run rn = t.run[lane];
+                double* dstg = Y + (size_t)rn.cell0 * KDp;
+                const unsigned sa = tma::smem_u32(ring + (size_t)s * prm.stage_doubles + (size_t)rn.scell * KDp);
+                if (accumulate) tma::bulk_red_add_f64(dstg, sa, (unsigned)rn.n * cell_bytes);
+                else tma::bulk_s2g(dstg, sa, (unsigned)rn.n * cell_bytes);
+            }
+            tma::bulk_commit();
+            if (it >= 1) {
+                bulk_wait_read1();                  // the previous tile's stage has been read out
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[8 + (it - 1) % NS]));
+            }
+            if (dbg && blockIdx.x == 0 && it < 64 && lane == 0) {
+                dbg[it * 8 + 3] = c0; dbg[it * 8 + 4] = c1; dbg[it * 8 + 5] = clock64();
+            }
+        }
+        tma::bulk_wait0();                          // every store has completed before the CTA exits
+    } else {
+        // ================= compute warps =================
+        const int ctid = tid - 64, ncth = 32 * STREAM_COMPUTE_WARPS;
+        for (int it = 0;; ++it) {
+            const int s = it % NS;
+            const long long w0 = clock64();
+            tma::mbar_wait(tma::smem_u32(&bars[s]), (unsigned)((it / NS) & 1));
+            const long long w1 = clock64();
+            const int P = sdesc[s].P, nr = sdesc[s].nr;
+            if (P < 0) {
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));      // pass the end marker on
+                break;
+            }
+            double* xs = ring + (size_t)s * prm.stage_doubles;
+            switch (P) {
+                case 0: short_tile_compute2<K, 0, 4>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 1: if constexpr (ShortDims<K>::pmax() >= 1) short_tile_compute2<K, 1, 2>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 2: if constexpr (ShortDims<K>::pmax() >= 2) short_tile_compute2<K, 2, 2>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+                case 3: if constexpr (ShortDims<K>::pmax() >= 3) short_tile_compute2<K, 3, 1>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
+            }
+            tma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));
+            if (dbg && blockIdx.x == 0 && it < 64 && ctid == 0) {
+                dbg[it * 8 + 6] = w1 - w0; dbg[it * 8 + 7] = clock64() - w1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic poles (any p, any K): a tile holds PT = nr * NPOLE poles; x is staged TRANSPOSED in
 // shared memory as xs[row = q*K+m][pole] so that lanes = poles read conflict-free; each thread
 // computes one block-row (K outputs) of one pole from the K x K block-CSR matrix (uniform,

@@ -22,7 +22,7 @@ buf = np.zeros(64 * 8, dtype=np.int64)
 lib.gsg_debug_stamps(plan._h, buf.ctypes.data_as(C.c_void_p), 64 * 8)
 b = buf.reshape(64, 8)
 t0 = b[0, 0]
-print("it | prod: wait_done  store_issue  wait_read  load_issue | comp: wait_full  compute | abs start")
-for it in range(40):
-    c0, c1, c2, c3, c4, w0, w1, w2 = b[it]
-    print(f"{it:2d} | {c1-c0:8d} {c2-c1:8d} {c3-c2:8d} {c4-c3:8d} | {w1-w0:8d} {w2-w1:8d} | {c0-t0:9d} {w0-t0:9d}")
+print("it | loader: wait_empty issue | storer: wait_done issue+free | compute: wait_full compute | loader abs")
+for it in range(44):
+    c0, c1, c2, s0, s1, s2, w, cmp_ = b[it]
+    print(f"{it:2d} | {c1-c0:8d} {c2-c1:8d} | {s1-s0:8d} {s2-s1:8d} | {w:8d} {cmp_:8d} | {c0-t0:9d}")

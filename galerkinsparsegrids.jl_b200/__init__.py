@@ -318,6 +318,10 @@ class Plan:
     def sync(self) -> None:
         check(lib.gsg_plan_sync(self._h))
 
+    def set_rk4_mode(self, mode: int) -> None:
+        """0 = automatic (Taylor form for the linear right-hand sides), 1 = always the staged form."""
+        check(lib.gsg_plan_set_rk4_mode(self._h, int(mode)))
+
     def set_shard(self, rank: int, nranks: int) -> None:
         check(lib.gsg_plan_set_shard(self._h, rank, nranks))
 

@@ -96,6 +96,8 @@ struct SweepClass {          // one launch of a sweep
     int nwarps = 8;          // long kernel: warps per CTA
     int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
     int cpl = 1;             // register-tiled long kernel: poles per lane
+    int npass = 1;           // ... and column passes
+    std::vector<std::unique_ptr<DevBuf<int>>> passBlk, passRow;
     DevBuf<TileL2> l2tiles;
     DevBuf<int> partBlk, partRow;
     size_t smem = 0;
@@ -138,6 +140,17 @@ struct gsg_plan {
     // long kernel: per p, the principal sub-block as a compact stream of block records
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
     std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
+    // register-tiled long kernel: column passes.  The principal sub-block of class p is cut into
+    // npass column slices (so that a 32*C-pole x tile of one slice fits shared memory); each slice is
+    // its own record stream with block columns relative to the slice
+    struct ColPass {
+        DevBuf<unsigned char> recs;
+        std::vector<int> row_start;      // first record of each block-row (+ end)
+        int qc0 = 0, nqc = 0;
+    };
+    std::map<std::pair<int, int>, std::vector<std::unique_ptr<ColPass>>> lpass;   // key (p, npass)
+    std::vector<int> h_rowptr, h_col;    // host copy of the block CSR
+    std::vector<double> h_val;
     // constant-bank kernel: per p, the pattern blocks' values in pattern order (empty = not usable)
     std::vector<std::vector<double>> consth_vals;
 
@@ -159,6 +172,11 @@ struct gsg_plan {
     DevBuf<int> tile_counter;     // dynamic tile scheduler of the persistent TMA kernel
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
+
+    // RK4 driver: 0 = automatic (linear right-hand sides use the Taylor form), 1 = always staged
+    int rk4_mode = 0;
+    cudaGraphExec_t step_exec = nullptr;     // last captured RK4 step (released with the plan / next capture)
+    DevBuf<double> wv4;
 
     // multi-GPU work sharing: this process launches tiles [rank*nt/nranks, (rank+1)*nt/nranks)
     int shard_rank = 0, shard_n = 1;
@@ -228,6 +246,9 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         }
         rowptr[q + 1] = (int)col.size();
     }
+    P.h_rowptr = rowptr;
+    P.h_col = col;
+    P.h_val = val;
     GSG_TRY(P.b_rowptr.upload(rowptr));
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
@@ -318,6 +339,51 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     P.htotal = (int)all.size();
     P.dense_host = all;
     GSG_TRY(P.dense_all.upload(all));
+    return 0;
+}
+
+// record streams of class p cut into npass column slices (cached per plan)
+int get_col_passes(gsg_plan& P, int p, int npass, const std::vector<std::unique_ptr<gsg_plan::ColPass>>** out) {
+    auto key = std::make_pair(p, npass);
+    auto it = P.lpass.find(key);
+    if (it == P.lpass.end()) {
+        const int K = P.S.k, KK = K * K;
+        const int REC = (KK * 8 + 8 + 15) & ~15;
+        const int nq = 1 << p;
+        std::vector<std::unique_ptr<gsg_plan::ColPass>> passes;
+        for (int ps = 0; ps < npass; ++ps) {
+            std::unique_ptr<gsg_plan::ColPass> cp(new gsg_plan::ColPass());
+            cp->nqc = nq / npass;
+            cp->qc0 = ps * cp->nqc;
+            std::vector<unsigned char> buf;
+            cp->row_start.assign(nq + 1, 0);
+            int nrec = 0;
+            for (int q = 0; q < nq; ++q) {
+                cp->row_start[q] = nrec;
+                std::vector<int> sel;
+                for (int b = P.h_rowptr[q]; b < P.h_rowptr[q + 1]; ++b)
+                    if (P.h_col[b] >= cp->qc0 && P.h_col[b] < cp->qc0 + cp->nqc) sel.push_back(b);
+                const int emit = std::max<int>((int)sel.size(), 1);       // every row owns an end-of-row record
+                for (int i = 0; i < emit; ++i) {
+                    buf.resize((size_t)(nrec + 1) * REC, 0);
+                    unsigned char* rec = buf.data() + (size_t)nrec * REC;
+                    int meta[2] = {0, i == emit - 1 ? 1 : 0};
+                    if (i < (int)sel.size()) {
+                        std::memcpy(rec, P.h_val.data() + (size_t)sel[i] * P.KK2, (size_t)KK * 8);
+                        meta[0] = P.h_col[sel[i]] - cp->qc0;
+                    }
+                    std::memcpy(rec + KK * 8, meta, 8);
+                    ++nrec;
+                }
+            }
+            cp->row_start[nq] = nrec;
+            buf.resize((size_t)(nrec + 2 * LONG_CH) * REC, 0);     // over-read slack for whole-chunk copies
+            GSG_TRY(cp->recs.upload(buf));
+            passes.push_back(std::move(cp));
+        }
+        it = P.lpass.emplace(key, std::move(passes)).first;
+    }
+    *out = &it->second;
     return 0;
 }
 
@@ -513,19 +579,29 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             if (ngrp == 0) continue;
             int C = K <= 3 ? 4 : 2;
             if (const char* e = getenv("GSG_LONG_C")) C = atoi(e);
-            // x tile: up to ~98 KB keeps two CTAs per SM; beyond that a CTA owns its SM anyway, so take
-            // the widest tile that fits (shared-memory wavefronts per DFMA fall with C)
+            while (C > 1 && 32 * (C >> 1) >= maxpoles) C >>= 1;                   // no wider than the groups
+            // the x tile of one column pass (NP / npass rows x 32*C poles) must fit shared memory: cut the
+            // matrix into column slices rather than narrow the tile (shared-memory wavefronts per DFMA fall
+            // with C; a pass costs one more read-modify-write of the class's y, which is small)
             size_t xcap = 200 * 1024;
             if (const char* e = getenv("GSG_LONG_XCAP")) xcap = (size_t)atoi(e) * 1024;
-            while (C > 1 && (size_t)NP * 32 * C * 8 > xcap) C >>= 1;
-            while (C > 1 && 32 * (C >> 1) >= maxpoles) C >>= 1;                   // no wider than the groups
+            int npass = 1;
+            while (npass < NQ && (size_t)(NP / npass) * 32 * C * 8 > xcap) npass <<= 1;
+            // Column passes are opt-in (GSG_LONG_PASSES=1): measured slower end to end at D=6 (the passes of
+            // one class run back to back on a handful of SMs and stretch the sweep's tail); by default the
+            // tile is narrowed instead.
+            if (!getenv("GSG_LONG_PASSES")) {
+                npass = 1;
+                while (C > 1 && (size_t)NP * 32 * C * 8 > xcap) C >>= 1;
+            }
+            const size_t xtile = (size_t)(NP / npass) * 32 * C * 8;
             // ~190 registers per thread at C = 4: small CTAs (several per SM) while the tile is small
-            int nw2 = (C >= 4 && (size_t)NP * 32 * C * 8 <= 100 * 1024) ? 4 : 8;
+            int nw2 = (C >= 4 && xtile <= 50 * 1024) ? 4 : 8;
             if (const char* e = getenv("GSG_LONG_NW")) nw2 = atoi(e);
             nw2 = std::max(1, std::min(nw2, 8));
             const size_t ring_bytes = (size_t)LONG_NBUF * LONG_CH * REC;
-            while (nw2 > 2 && (size_t)NP * 32 * C * 8 + nw2 * ring_bytes + 2048 > SMEM_OPTIN_MAX) nw2 >>= 1;
-            const size_t smem2 = (size_t)NP * 32 * C * 8 + nw2 * ring_bytes;
+            while (nw2 > 2 && xtile + nw2 * ring_bytes + 2048 > SMEM_OPTIN_MAX) nw2 >>= 1;
+            const size_t smem2 = xtile + nw2 * ring_bytes;
             if (smem2 + 2048 <= SMEM_OPTIN_MAX && (C == 1 || C == 2 || C == 4)) {
                 c.kind = Kind::LONG2;
                 c.cpl = C;
@@ -560,20 +636,25 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
                         base.push_back(t);
                     }
                 }
-                // row parts: enough CTAs to fill the GPU, at least two block-rows per warp
-                const std::vector<int>& rs = P.lrow_start[p];
-                const int nrec = rs[NQ];
                 // row parts: the x tile is staged once per part, so as few parts as keep one CTA's record
                 // stream short enough to finish well inside the sweep (the long classes run beside the
                 // streaming kernel; their SM time, not their latency, is what counts)
-                int rsplit = (nrec + 1399) / 1400;
+                const std::vector<std::unique_ptr<gsg_plan::ColPass>>* passes = nullptr;
+                GSG_TRY(get_col_passes(P, p, npass, &passes));
+                c.npass = npass;
+                int maxrec = 0;
+                for (const auto& cp : *passes) maxrec = std::max(maxrec, cp->row_start[NQ]);
+                const int reccap = std::max(128, 1400 / npass);       // passes run back to back: keep each short
+                int rsplit = (maxrec + reccap - 1) / reccap;
                 if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
                 rsplit = std::max(1, std::min(rsplit, std::max(1, NQ / (2 * nw2))));
                 c.rsplit = rsplit;
                 const int G = rsplit * nw2;
-                std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
-                pb[0] = 0; pr[0] = 0;
-                {
+                for (const auto& cp : *passes) {
+                    const std::vector<int>& rs = cp->row_start;
+                    const int nrec = rs[NQ];
+                    std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
+                    pb[0] = 0; pr[0] = 0;
                     const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
                     int q = 0;
                     for (int g = 1; g < G; ++g) {
@@ -582,9 +663,11 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
                         pr[g] = std::max(q, pr[g - 1]);
                         pb[g] = rs[pr[g]];
                     }
+                    c.passBlk.emplace_back(new DevBuf<int>());
+                    c.passRow.emplace_back(new DevBuf<int>());
+                    GSG_TRY(c.passBlk.back()->upload(pb));
+                    GSG_TRY(c.passRow.back()->upload(pr));
                 }
-                GSG_TRY(c.partBlk.upload(pb));
-                GSG_TRY(c.partRow.upload(pr));
                 std::vector<TileL2> full;
                 full.reserve(base.size() * rsplit);
                 for (int part = 0; part < rsplit; ++part)
@@ -734,6 +817,12 @@ int launch_check(const char* what, int K, const SweepClass& c) {
 
 template <class Kern>
 int ensure_smem(Kern kern, size_t smem, size_t& configured) {
+    if (configured == 0) {
+        // every sweep kernel asks for the maximum shared-memory carve-out: kernels with different
+        // carve-outs cannot be resident on one SM at the same time
+        GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = 1;
+    }
     if (smem > 32 * 1024 && smem > configured) {      // static + dynamic must stay under 48 KB without opt-in
         GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -838,10 +927,16 @@ int launch_long2_kc(gsg_plan& pl, cudaStream_t st, const Direction& dir, const S
     tile_range(pl, c.ntiles, tb, tn);
     if (tn == 0) return 0;
     const int PI = (int)pl.S.kD / K;
-    kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.offtab.p,
-                                             c.l2tiles.p + tb, pl.lrec[c.p]->p, c.partBlk.p, c.partRow.p, c.p,
-                                             (int)pl.S.kDp, dir.A, PI, pl.dbg);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    auto it = pl.lpass.find(std::make_pair(c.p, c.npass));
+    if (it == pl.lpass.end()) return fail(GSG_ERR_UNSUPPORTED, "internal: column passes missing");
+    for (int ps = 0; ps < c.npass; ++ps) {        // passes accumulate into the same y: same stream, in order
+        const gsg_plan::ColPass& cp = *it->second[ps];
+        kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, (beta != 0.0 || ps > 0) ? 1 : 0, dir.celltab.p,
+                                                 dir.offtab.p, c.l2tiles.p + tb, cp.recs.p, c.passBlk[ps]->p,
+                                                 c.passRow[ps]->p, c.p, cp.qc0, cp.nqc, (int)pl.S.kDp, dir.A, PI,
+                                                 pl.dbg);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return launch_check("sweep_long2", K, c);
 }
 
@@ -875,7 +970,7 @@ int launch_consth_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
     const int PI = (int)pl.S.kD / K;
     const int grid = (tn + CONSTH_WARPS - 1) / CONSTH_WARPS;
     kern<<<grid, 32 * CONSTH_WARPS, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.offtab.p,
-                                                   c.l2tiles.p + tb, tn, (int)pl.S.kDp, dir.A, PI, hb);
+                                                   c.l2tiles.p + tb, tn, (int)pl.S.kDp, dir.A, PI, hb, pl.dbg);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return launch_check("sweep_consth", K, c);
 }
@@ -952,12 +1047,17 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     // forked launches first: the long-pole CTAs should be resident before the persistent
     // streaming kernel occupies every SM
     static const int only = getenv("GSG_ONLY_CLASS") ? atoi(getenv("GSG_ONLY_CLASS")) : -1;   // timing aid
+    static const int cmask = getenv("GSG_CLASS_MASK") ? atoi(getenv("GSG_CLASS_MASK")) : -1;  // timing aid (bit i = class i)
+    static const bool stream_first = getenv("GSG_STREAM_FIRST") != nullptr;
+    if (stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1)))
+        GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
     for (size_t i = 1; i < nc; ++i) {
         if (only >= 0 && (int)i != only) continue;
+        if (cmask >= 0 && !((cmask >> i) & 1)) continue;
         cudaStream_t st = fork ? pl.aux[i] : pl.stream;
         GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
     }
-    if (nc > 0 && (only < 0 || only == 0)) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    if (!stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1))) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
     if (fork) {
         for (size_t i = 1; i < nc; ++i) {
             GSG_CUDA(cudaEventRecord(pl.ev_done[i], pl.aux[i]));
@@ -987,6 +1087,39 @@ int laplacian(gsg_plan& pl, const double* u, double* k, double* tmp) {
     return 0;
 }
 
+// Runs `one_step` nsteps times on pl.stream.  The first step runs eagerly (it also configures the
+// kernels' attributes); the second is captured into a CUDA graph (the sweeps' stream fork/join becomes
+// graph dependencies) and the rest replay it, so the ~270 launches of a step cost no host time.
+template <class Step>
+int run_steps(gsg_plan& pl, int64_t nsteps, Step one_step) {
+    // Opt-in (GSG_GRAPH=1): measured SLOWER at D=6 (6.2 vs 5.4 ms per step) -- inside a graph the
+    // independent kernel nodes of a sweep lose their launch order and stream priorities, the persistent
+    // streaming kernel takes every SM first and the long-pole kernels run after it instead of beside it.
+    const bool use_graph = nsteps >= 3 && !pl.prof_on && !pl.dbg && getenv("GSG_GRAPH") != nullptr;
+    if (!use_graph) {
+        for (int64_t s = 0; s < nsteps; ++s) GSG_TRY(one_step());
+        return 0;
+    }
+    GSG_TRY(one_step());
+    if (pl.step_exec) { cudaGraphExecDestroy(pl.step_exec); pl.step_exec = nullptr; }
+    const int64_t l0 = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    GSG_CUDA(cudaStreamBeginCapture(pl.stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = one_step();
+    const cudaError_t ce = cudaStreamEndCapture(pl.stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(GSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const int64_t per_step = g_launches.load() - l0;
+    g_launches.fetch_sub(per_step, std::memory_order_relaxed);          // the capture launched nothing
+    const cudaError_t ie = cudaGraphInstantiate(&pl.step_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(GSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    for (int64_t s = 1; s < nsteps; ++s) GSG_CUDA(cudaGraphLaunch(pl.step_exec, pl.stream));
+    g_launches.fetch_add(per_step * (nsteps - 1), std::memory_order_relaxed);
+    return 0;
+}
+
+// Classical RK4 in its staged form; works for any right-hand side.
 template <class Rhs>
 int rk4_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nsteps, Rhs rhs) {
     GSG_TRY(pl.wk.resize(len));
@@ -996,7 +1129,7 @@ int rk4_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nsteps, Rh
     double* acc = pl.wacc.p;
     double* w = pl.ww.p;
     const int grid = elementwise_grid(pl, len);
-    for (int64_t s = 0; s < nsteps; ++s) {
+    return run_steps(pl, nsteps, [&]() -> int {
         GSG_TRY(rhs(y, k));                                                        // k1
         rk_stage_kernel<<<grid, 256, 0, pl.stream>>>(len, y, k, acc, w, 0.5 * dt, dt / 6.0, 1);
         GSG_TRY(rhs(w, k));                                                        // k2
@@ -1007,8 +1140,37 @@ int rk4_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nsteps, Rh
         rk_final_kernel<<<grid, 256, 0, pl.stream>>>(len, y, k, acc, dt / 6.0);
         g_launches.fetch_add(4, std::memory_order_relaxed);
         GSG_CUDA(cudaGetLastError());
-    }
-    return 0;
+        return 0;
+    });
+}
+
+// Classical RK4 for a LINEAR, time-independent right-hand side f(u) = L u.  The four stages are then
+// k1 = L u, k2 = k1 + dt/2 L k1, ... and the update collapses to
+//   u += dt L u + dt^2/2 L^2 u + dt^3/6 L^3 u + dt^4/24 L^4 u
+// -- the same four operator applications, but one combine pass (48 B per DOF) instead of three stage
+// updates and a final one (144 B per DOF).  Identical to the staged form up to rounding.
+template <class Rhs>
+int rk4_linear_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nsteps, Rhs rhs) {
+    GSG_TRY(pl.wk.resize(len));
+    GSG_TRY(pl.wacc.resize(len));
+    GSG_TRY(pl.ww.resize(len));
+    GSG_TRY(pl.wv4.resize(len));
+    double* v1 = pl.wk.p;
+    double* v2 = pl.wacc.p;
+    double* v3 = pl.ww.p;
+    double* v4 = pl.wv4.p;
+    const int grid = elementwise_grid(pl, len);
+    return run_steps(pl, nsteps, [&]() -> int {
+        GSG_TRY(rhs(y, v1));
+        GSG_TRY(rhs(v1, v2));
+        GSG_TRY(rhs(v2, v3));
+        GSG_TRY(rhs(v3, v4));
+        rk4_taylor_kernel<<<grid, 256, 0, pl.stream>>>(len, y, v1, v2, v3, v4, dt, dt * dt / 2.0, dt * dt * dt / 6.0,
+                                                        dt * dt * dt * dt / 24.0);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        GSG_CUDA(cudaGetLastError());
+        return 0;
+    });
 }
 
 int check_plan(const gsg_plan* p) {
@@ -1158,6 +1320,7 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     GSG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
     int prio_lo = 0, prio_hi = 0;     // long-pole CTAs first: they run beside the persistent streaming kernel
     GSG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("GSG_NO_PRIO")) prio_hi = prio_lo;
     P->aux.assign(n + 3, nullptr);
     P->ev_done.assign(n + 3, nullptr);
     for (int i = 0; i < n + 3; ++i) {
@@ -1197,6 +1360,7 @@ int gsg_plan_destroy(gsg_plan* plan) {
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     for (auto& pr : plan->prof_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (plan->step_exec) cudaGraphExecDestroy(plan->step_exec);
     delete plan;
     return 0;
 }
@@ -1235,6 +1399,12 @@ int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_lay
     GSG_TRY(check_plan(plan));
     if (!ref_layout_dev || !dev_layout_dev) return fail(GSG_ERR_ARG, "null pointer");
     return copy_out(*plan, ref_layout_dev, dev_layout_dev, cudaMemcpyDeviceToDevice);
+}
+
+int gsg_plan_set_rk4_mode(gsg_plan* plan, int mode) {
+    if (!plan || (mode != 0 && mode != 1)) return fail(GSG_ERR_ARG, "rk4 mode must be 0 (automatic) or 1 (staged)");
+    plan->rk4_mode = mode;
+    return 0;
 }
 
 int gsg_plan_set_shard(gsg_plan* plan, int rank, int nranks) {
@@ -1299,13 +1469,25 @@ int gsg_profile_read(gsg_plan* plan, int64_t* launches_out, double* total_ms_out
 int gsg_debug_stamps(gsg_plan* plan, long long* out, int n) {
     GSG_TRY(check_plan(plan));
     if (!plan->dbg) {
-        GSG_TRY(plan->dbgbuf.resize(64 * 8));
-        cudaMemset(plan->dbgbuf.p, 0, 64 * 8 * sizeof(long long));
+        GSG_TRY(plan->dbgbuf.resize(8192));
+        cudaMemset(plan->dbgbuf.p, 0, 8192 * sizeof(long long));
         plan->dbg = plan->dbgbuf.p;
         return 0;
     }
     GSG_CUDA(cudaDeviceSynchronize());
-    if (out && n > 0) GSG_CUDA(cudaMemcpy(out, plan->dbg, sizeof(long long) * std::min(n, 64 * 8), cudaMemcpyDeviceToHost));
+    if (out && n > 0) GSG_CUDA(cudaMemcpy(out, plan->dbg, sizeof(long long) * std::min(n, 8192), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// development aid: launch a spinner (threads, dynamic smem, duration) on the main (which = 0) or first
+// auxiliary stream (which = 1); its CTAs stamp {smid, start, end} into the debug buffer at `slot`
+int gsg_debug_spin(gsg_plan* plan, int which, int grid, int threads, int smem, int ns, int slot) {
+    GSG_TRY(check_plan(plan));
+    if (!plan->dbg) return fail(GSG_ERR_ARG, "enable gsg_debug_stamps first");
+    GSG_CUDA(cudaFuncSetAttribute(debug_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaStream_t st = which ? plan->aux[1] : plan->stream;
+    debug_spin_kernel<<<grid, threads, smem, st>>>(plan->dbg, slot, ns);
+    GSG_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -1376,8 +1558,9 @@ int gsg_rk4_advect_dev(gsg_plan* plan, const double* a, double* y_dev, double dt
     if (!a || !y_dev || nsteps < 0) return fail(GSG_ERR_ARG, "bad argument");
     std::vector<double> av(a, a + plan->S.D);
     gsg_plan& pl = *plan;
-    return rk4_loop(pl, plan->S.Npad, y_dev, dt, nsteps,
-                    [&](const double* w, double* k) { return advect_rhs(pl, av.data(), w, k); });
+    auto rhs = [&](const double* w, double* k) { return advect_rhs(pl, av.data(), w, k); };
+    if (pl.rk4_mode == 0) return rk4_linear_loop(pl, plan->S.Npad, y_dev, dt, nsteps, rhs);
+    return rk4_loop(pl, plan->S.Npad, y_dev, dt, nsteps, rhs);
 }
 
 int gsg_rk4_advect(gsg_plan* plan, const double* a, double* y, double dt, int64_t nsteps) {
@@ -1402,11 +1585,12 @@ int gsg_rk4_wave_dev(gsg_plan* plan, double* u_dev, double* v_dev, double dt, in
     double* y = pl.wy.p;
     GSG_CUDA(cudaMemcpyAsync(y, u_dev, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
     GSG_CUDA(cudaMemcpyAsync(y + Np, v_dev, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
-    int rc = rk4_loop(pl, 2 * Np, y, dt, nsteps, [&](const double* w, double* k) {
+    auto rhs = [&](const double* w, double* k) -> int {
         // [u; v]' = [v; L u]   (src/pdes.jl:22-49)
         GSG_CUDA(cudaMemcpyAsync(k, w + Np, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
         return laplacian(pl, w, k + Np, pl.wtmp.p);
-    });
+    };
+    int rc = pl.rk4_mode == 0 ? rk4_linear_loop(pl, 2 * Np, y, dt, nsteps, rhs) : rk4_loop(pl, 2 * Np, y, dt, nsteps, rhs);
     if (rc) return rc;
     GSG_CUDA(cudaMemcpyAsync(u_dev, y, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));
     GSG_CUDA(cudaMemcpyAsync(v_dev, y + Np, Np * sizeof(double), cudaMemcpyDeviceToDevice, pl.stream));

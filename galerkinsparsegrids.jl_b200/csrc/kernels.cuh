@@ -172,6 +172,9 @@ struct ShortParams {
     int nstage;
 };
 
+__device__ __forceinline__ unsigned smid_u32() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ long long gtimer() { long long r; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r)); return r; }
+
 namespace tma {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -535,6 +538,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int NS = prm.nstage;            // <= 4
+    const long long g_t0 = dbg ? gtimer() : 0;
     const int KDp = prm.KDp;
     const unsigned cell_bytes = (unsigned)KDp * 8u;
 
@@ -630,6 +634,10 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
             }
         }
         tma::bulk_wait0();                          // every store has completed before the CTA exits
+        if (dbg && lane == 0 && blockIdx.x < 512) {
+            long long* o = dbg + 4096 + blockIdx.x * 4;
+            o[0] = smid_u32(); o[1] = g_t0; o[2] = gtimer(); o[3] = it;
+        }
     } else {
         // ================= compute warps =================
         const int ctid = tid - 64, ncth = 32 * STREAM_COMPUTE_WARPS;
@@ -991,14 +999,17 @@ __global__ void __launch_bounds__(256)
 sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                    const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
                    const TileL2* __restrict__ tiles, const unsigned char* __restrict__ recs,
-                   const int* __restrict__ partBlk, const int* __restrict__ partRow, int p, int KDp, int A, int PI,
+                   const int* __restrict__ partBlk, const int* __restrict__ partRow, int p,
+                   int qc0, int nqc,                   // column pass: block columns [qc0, qc0 + nqc) of the matrix
+                   int KDp, int A, int PI,
                    long long* __restrict__ dbg) {     // dbg: optional per-warp clock stamps (first 8 CTAs)
     constexpr int KK = K * K, REC = LongRec<K>::BYTES;
     constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
     constexpr int RINGREC = LONG_CH * LONG_NBUF;              // records the ring holds
     constexpr int PT = 32 * C;
     const long long t_start = clock64();
-    const int NQ = 1 << p, NP = K * NQ;
+    const long long g_t0 = dbg ? gtimer() : 0;
+    const int NP = K * nqc;                                   // x rows staged by this pass
     extern __shared__ __align__(128) unsigned char smraw[];
 
     const TileL2 t = tiles[blockIdx.x];
@@ -1050,8 +1061,8 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     }
 
     // ---- stage the x tile in (asynchronous 8-byte copies, coalesced per (cell, mode, c))
-    for (int qq = warp; qq < NQ; qq += nwarp) {
-        const CellOfs co = ctab[qq];
+    for (int qq = warp; qq < nqc; qq += nwarp) {
+        const CellOfs co = ctab[qc0 + qq];
         const unsigned dst = xs_s + qq * (K * PT * 8);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -1152,6 +1163,13 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     if (dbg && blockIdx.x < 8 && lane == 0) {
         long long* o = dbg + (blockIdx.x * 8 + warp) * 8;
         o[0] = t_start; o[1] = t_issued; o[2] = t_staged; o[3] = clock64(); o[4] = b1 - b0; o[5] = q - partRow[gpart];
+    }
+    if (dbg && tid == 0) {          // CTA placement log: {smid, start, end, class tag}
+        const int slot = atomicAdd(reinterpret_cast<int*>(dbg + 1023), 1);
+        if (slot < 500) {
+            long long* o = dbg + 6144 + slot * 4;
+            o[0] = smid_u32(); o[1] = g_t0; o[2] = gtimer(); o[3] = p * 100 + qc0 / (nqc > 0 ? nqc : 1);
+        }
     }
 }
 
@@ -1270,14 +1288,18 @@ __global__ void __launch_bounds__(32 * CONSTH_WARPS)
 sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                     const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
                     const TileL2* __restrict__ tiles, int ntiles, int KDp, int A, int PI,
-                    const __grid_constant__ HBlocks<K, P> hb) {
+                    const __grid_constant__ HBlocks<K, P> hb, long long* __restrict__ dbg) {
     constexpr int NQ = 1 << P, NP = K * NQ;
+    const long long g_t0 = dbg ? gtimer() : 0;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int warp = threadIdx.x >> 5;
     int lane = threadIdx.x & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    // warps are independent (no CTA-wide barrier below), one tile each.  (A persistent variant -- grid
+    // stride loop, <= 128 registers -- does share SMs with the streaming kernel, but costs 40 more
+    // registers or spills and was slower end to end)
     const int ti = blockIdx.x * CONSTH_WARPS + warp;
-    if (ti >= ntiles) return;                       // warps are independent: no CTA-wide barrier below
+    if (ti >= ntiles) return;
     const TileL2 t = tiles[ti];
     unsigned char* wbase = smraw + (size_t)warp * (NP * 32 * 8 + NQ * sizeof(CellOfs));
     CellOfs* ctab_s = reinterpret_cast<CellOfs*>(wbase + NP * 32 * 8);
@@ -1329,6 +1351,23 @@ sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     cp_async_wait<0>();
     __syncwarp();
     consth_rows<K, P, 0>(hb, cx, rowofs, yold);
+    if (dbg && threadIdx.x == 0 && blockIdx.x < 512) {
+        long long* o = dbg + 1024 + blockIdx.x * 4;
+        o[0] = smid_u32(); o[1] = g_t0; o[2] = gtimer();
+    }
+}
+
+// development aid: a spinner with a chosen resource footprint, to probe which kernels share an SM
+__global__ void debug_spin_kernel(long long* __restrict__ dbg, int slot, int ns) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const long long t0 = gtimer();
+    double a = threadIdx.x;
+    while (gtimer() - t0 < ns) a = a * 1.0000001 + 1e-9;
+    smraw[threadIdx.x] = (unsigned char)a;
+    if (threadIdx.x == 0 && blockIdx.x < 512) {
+        long long* o = dbg + slot + blockIdx.x * 4;
+        o[0] = smid_u32(); o[1] = t0; o[2] = gtimer(); o[3] = (long long)a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1354,6 +1393,21 @@ __global__ void rk_final_kernel(long long N, double* __restrict__ u, const doubl
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
         u[i] = fma(ca, k[i], acc[i]);
+}
+
+// u += c1 v1 + c2 v2 + c3 v3 + c4 v4   (Taylor form of RK4 for linear right-hand sides; summed
+// smallest term first)
+__global__ void rk4_taylor_kernel(long long N, double* __restrict__ u, const double* __restrict__ v1,
+                                  const double* __restrict__ v2, const double* __restrict__ v3,
+                                  const double* __restrict__ v4, double c1, double c2, double c3, double c4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        double s = c4 * v4[i];
+        s = fma(c3, v3[i], s);
+        s = fma(c2, v2[i], s);
+        s = fma(c1, v1[i], s);
+        u[i] += s;
+    }
 }
 
 __global__ void scale_kernel(long long N, double* __restrict__ y, double beta) {

@@ -106,6 +106,11 @@ int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, do
 int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, double* y_dev);
 int gsg_apply_laplacian_dev(gsg_plan* plan, const double* x_dev, double* y_dev, double* tmp_dev);
 
+/* RK4 driver variant: 0 (default) = automatic -- the linear right-hand sides below are advanced in the
+ * Taylor form u += dt L u + dt^2/2 L^2 u + dt^3/6 L^3 u + dt^4/24 L^4 u (same four operator applies,
+ * one combine pass; identical to the staged form up to rounding); 1 = always the staged form. */
+int gsg_plan_set_rk4_mode(gsg_plan* plan, int mode);
+
 /* ---- fused fixed-step RK4 evolutions, state resident on device ------------------------- */
 /* u' = -sum_d a[d] D_d u  (the operator vlasov_evolve applies, src/pdes.jl:179-180;
  * BASELINE config 4).  Classical RK4, stage order in DESIGN.md.  y is updated in place. */

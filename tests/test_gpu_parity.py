@@ -112,6 +112,25 @@ def test_rk4_advect_fixed_steps(plans, oracle, D, k, n, f):
     assert relerr(out, u0) > 1e-6          # the state actually moved
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rk4_modes_agree_with_oracle(plans, oracle, mode):
+    """Both RK4 drivers -- Taylor form for linear right-hand sides (mode 0) and the staged form (mode 1),
+    each replayed from a captured CUDA graph after the first step -- against the oracle's classical RK4."""
+    D, k, n = 3, 3, 4
+    plan, H = plans(D, k, n, "sparse")
+    u0 = product_state(oracle, D, k, n, f_gauss)
+    a = np.array([1.0, -0.5, 0.25])
+    mats = [oracle.D_matrix_poles(D, d, k, n, H=H) for d in range(1, D + 1)]
+    dt, nsteps = 1.0e-4, 24
+    ref = oracle.rk4(oracle.advect_rhs(mats, a), u0, dt, nsteps)
+    plan.set_rk4_mode(mode)
+    try:
+        out = plan.rk4_advect(a, u0, dt, nsteps)
+    finally:
+        plan.set_rk4_mode(0)
+    assert relerr(out, ref) <= TOL
+
+
 def test_rk4_wave_fixed_steps(plans, oracle):
     D, k, n = 2, 3, 5
     plan, H = plans(D, k, n, "sparse")

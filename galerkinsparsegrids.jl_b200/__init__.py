@@ -322,6 +322,32 @@ class Plan:
         """0 = automatic (Taylor form for the linear right-hand sides), 1 = always the staged form."""
         check(lib.gsg_plan_set_rk4_mode(self._h, int(mode)))
 
+    def set_partition(self, rank: int, nranks: int) -> None:
+        """Block partition over nranks = 2^b ranks (include/gsg_b200.h): afterwards the plan's sweeps
+        cover only the pole groups this rank computes."""
+        check(lib.gsg_plan_set_partition(self._h, int(rank), int(nranks)))
+
+    @property
+    def cell_stride(self) -> int:
+        """doubles per multi-cell in the device layout (k^D rounded up to even)"""
+        kd = self.k ** self.D
+        return kd + (kd & 1)
+
+    def partition_blocks(self, kind: int, d: int = 0):
+        """(offsets, sizes, partner): kind 0 = blocks this rank owns, kind 1 = level_d == 0 blocks exchanged
+        with `partner` along partition dimension d (empty if d is not one)."""
+        cnt, partner = C.c_int64(), C.c_int(-1)
+        check(lib.gsg_plan_partition_blocks(self._h, kind, d, None, None, C.byref(cnt), C.byref(partner)))
+        offs = np.zeros(max(cnt.value, 1), dtype=np.int64)
+        sizes = np.zeros(max(cnt.value, 1), dtype=np.int64)
+        check(lib.gsg_plan_partition_blocks(self._h, kind, d, _ptr(offs), _ptr(sizes), C.byref(cnt), C.byref(partner)))
+        return offs[:cnt.value], sizes[:cnt.value], partner.value
+
+    def rk4_taylor_cells_dev(self, cells, u, v1, v2, v3, v4, c1, c2, c3, c4) -> None:
+        check(lib.gsg_rk4_taylor_cells_dev(self._h, _devptr(cells), int(cells.numel()), _devptr(u), _devptr(v1),
+                                           _devptr(v2), _devptr(v3), _devptr(v4), float(c1), float(c2), float(c3),
+                                           float(c4)))
+
     def set_shard(self, rank: int, nranks: int) -> None:
         check(lib.gsg_plan_set_shard(self._h, rank, nranks))
 

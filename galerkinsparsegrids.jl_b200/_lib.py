@@ -67,6 +67,9 @@ SIGNATURES = {
     "gsg_rk4_wave_dev": (i32, [vp, vp, vp, f64, i64]),
     "gsg_energy": (i32, [vp, vp, vp, p_f64]),
     "gsg_plan_set_shard": (i32, [vp, i32, i32]),
+    "gsg_plan_set_partition": (i32, [vp, i32, i32]),
+    "gsg_plan_partition_blocks": (i32, [vp, i32, i32, vp, vp, p_i64, C.POINTER(i32)]),
+    "gsg_rk4_taylor_cells_dev": (i32, [vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64]),
     "gsg_plan_set_rk4_mode": (i32, [vp, i32]),
     "gsg_rk_stage_dev": (i32, [vp, i64, vp, vp, vp, vp, f64, f64, i32]),
     "gsg_rk_final_dev": (i32, [vp, i64, vp, vp, vp, f64]),

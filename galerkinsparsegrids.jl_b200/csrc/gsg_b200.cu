@@ -178,6 +178,10 @@ struct gsg_plan {
     cudaGraphExec_t step_exec = nullptr;     // last captured RK4 step (released with the plan / next capture)
     DevBuf<double> wv4;
 
+    // multi-GPU block partition (gsg_plan_set_partition): part_bits dimensions D, D-1, ... each split the
+    // multi-level blocks into {level == 0} and {level >= 1}; rank bit j = 1 owns level_{D-j} == 0
+    int part_rank = 0, part_bits = 0;
+
     // multi-GPU work sharing: this process launches tiles [rank*nt/nranks, (rank+1)*nt/nranks)
     int shard_rank = 0, shard_n = 1;
 
@@ -418,6 +422,17 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
         if (Slo * Shi > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many items in a pole group");
         g.S = (int)Slo;
         g.nitems = (int)(Slo * Shi);
+        // block partition: this rank sweeps a group iff it owns it.  Along a partition dimension a pole
+        // with p >= 1 straddles the pair of ranks that differ in that bit; the rank holding level >= 1
+        // (bit 0) sweeps it after receiving the level-0 cells, p == 0 poles stay with the bit-1 rank.
+        bool mine = true;
+        for (int j = 0; j < P.part_bits; ++j) {
+            const int e = D - 1 - j;
+            const int mybit = (P.part_rank >> j) & 1;
+            if (e == d) mine = mine && (g.p == 0 ? mybit == 1 : mybit == 0);
+            else mine = mine && ((b0.level[e] == 0) == (mybit == 1));
+        }
+        if (!mine) continue;
         groups.push_back(g);
     }
     GSG_TRY(dir.groups.upload(groups));
@@ -1051,13 +1066,25 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     static const bool stream_first = getenv("GSG_STREAM_FIRST") != nullptr;
     if (stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1)))
         GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    // GSG_CONSTH_LAST: the constant-bank class is launched AFTER the streaming kernel (its small CTAs can
+    // share an SM with a streaming CTA when the latter runs three stages)
+    static const bool consth_last = getenv("GSG_CONSTH_LAST") != nullptr;
     for (size_t i = 1; i < nc; ++i) {
         if (only >= 0 && (int)i != only) continue;
         if (cmask >= 0 && !((cmask >> i) & 1)) continue;
+        if (consth_last && dir.classes[i].kind == Kind::CONSTH) continue;
         cudaStream_t st = fork ? pl.aux[i] : pl.stream;
         GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
     }
     if (!stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1))) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    if (consth_last)
+        for (size_t i = 1; i < nc; ++i) {
+            if (dir.classes[i].kind != Kind::CONSTH) continue;
+            if (only >= 0 && (int)i != only) continue;
+            if (cmask >= 0 && !((cmask >> i) & 1)) continue;
+            cudaStream_t st = fork ? pl.aux[i] : pl.stream;
+            GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
+        }
     if (fork) {
         for (size_t i = 1; i < nc; ++i) {
             GSG_CUDA(cudaEventRecord(pl.ev_done[i], pl.aux[i]));
@@ -1404,6 +1431,93 @@ int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_lay
 int gsg_plan_set_rk4_mode(gsg_plan* plan, int mode) {
     if (!plan || (mode != 0 && mode != 1)) return fail(GSG_ERR_ARG, "rk4 mode must be 0 (automatic) or 1 (staged)");
     plan->rk4_mode = mode;
+    return 0;
+}
+
+// ---- multi-GPU block partition ----------------------------------------------------------------------
+int gsg_plan_set_partition(gsg_plan* plan, int rank, int nranks) {
+    GSG_TRY(check_plan(plan));
+    int bits = 0;
+    while ((1 << bits) < nranks) ++bits;
+    if (nranks < 1 || (1 << bits) != nranks || bits > plan->S.D || rank < 0 || rank >= nranks)
+        return fail(GSG_ERR_ARG, "partition: nranks must be a power of two <= 2^D and 0 <= rank < nranks");
+    GSG_CUDA(cudaStreamSynchronize(plan->stream));
+    plan->part_rank = rank;
+    plan->part_bits = bits;
+    plan->dirs.clear();
+    plan->dirs.resize(plan->S.D);
+    for (int d = 0; d < plan->S.D; ++d) GSG_TRY(build_direction(*plan, d));
+    return 0;
+}
+
+static int block_owner(const gsg_plan& pl, const gsg::Block& b, int skip_dim /* -1: none */) {
+    int o = 0;
+    for (int j = 0; j < pl.part_bits; ++j) {
+        const int e = pl.S.D - 1 - j;
+        if (e == skip_dim) continue;
+        if (b.level[e] == 0) o |= 1 << j;
+    }
+    return o;
+}
+
+// kind 0: the blocks this rank owns.  kind 1 (d = 1-based partition dimension): the level_d == 0 blocks of
+// the poles that straddle this rank and its partner along d -- the partner pair exchanges exactly these
+// (their owner sends the stage input, the sweeping rank returns its contribution).  Offsets and sizes are
+// in doubles of the DEVICE layout.  Two-call pattern: offsets == NULL returns the count only.
+int gsg_plan_partition_blocks(gsg_plan* plan, int kind, int d, int64_t* offsets, int64_t* sizes, int64_t* count,
+                              int* partner_out) {
+    if (!plan || !count) return fail(GSG_ERR_ARG, "null pointer");
+    const gsg_plan& pl = *plan;
+    const int D = pl.S.D;
+    int bitj = -1;
+    if (kind == 1) {
+        if (d < 1 || d > D) return fail(GSG_ERR_ARG, "axis d out of range [1,D]");
+        bitj = D - d;                                  // dimension d (1-based) carries bit D - d
+        if (bitj >= pl.part_bits) {                    // not a partition dimension: nothing to exchange
+            *count = 0;
+            if (partner_out) *partner_out = -1;
+            return 0;
+        }
+        if (partner_out) *partner_out = pl.part_rank ^ (1 << bitj);
+    } else if (kind != 0) {
+        return fail(GSG_ERR_ARG, "kind must be 0 or 1");
+    }
+    const int others_mask = kind == 1 ? ~(1 << bitj) : ~0;
+    int64_t nout = 0;
+    for (const gsg::Block& b : pl.S.blocks) {
+        bool take;
+        if (kind == 0) {
+            take = block_owner(pl, b, -1) == pl.part_rank;
+        } else {
+            int s = 0;
+            for (int i = 0; i < D; ++i) s += b.level[i];
+            const bool straddles = pl.S.scheme == 1 ? pl.S.n >= 1 : s < pl.S.n;      // pole has p >= 1
+            take = b.level[d - 1] == 0 && straddles &&
+                   ((block_owner(pl, b, d - 1) ^ pl.part_rank) & others_mask & ((1 << pl.part_bits) - 1)) == 0;
+        }
+        if (!take) continue;
+        if (offsets) {
+            offsets[nout] = b.poffset;
+            sizes[nout] = b.ncells * pl.S.kDp;
+        }
+        ++nout;
+    }
+    *count = nout;
+    return 0;
+}
+
+// u[c] += c1 v1[c] + ... + c4 v4[c] on the listed multi-cells (device layout; cells = multi-cell indices)
+int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncells, double* u, const double* v1,
+                             const double* v2, const double* v3, const double* v4, double c1, double c2, double c3,
+                             double c4) {
+    GSG_TRY(check_plan(plan));
+    if (!cells_dev || !u || !v1 || !v2 || !v3 || !v4 || ncells < 0) return fail(GSG_ERR_ARG, "bad argument");
+    if (ncells == 0) return 0;
+    const int grid = (int)std::min<int64_t>(ncells, (int64_t)plan->sm_count * 16);
+    rk4_taylor_cells_kernel<<<grid, 256, 0, plan->stream>>>(cells_dev, ncells, (int)plan->S.kDp, u, v1, v2, v3, v4, c1,
+                                                            c2, c3, c4);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GSG_CUDA(cudaGetLastError());
     return 0;
 }
 

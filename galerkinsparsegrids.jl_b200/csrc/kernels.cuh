@@ -1160,7 +1160,7 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
         if (++i >= b1) break;
     }
     cp_async_wait<0>();
-    if (dbg && blockIdx.x < 8 && lane == 0) {
+    if (dbg && blockIdx.x < 8 && lane == 0 && warp < 8) {
         long long* o = dbg + (blockIdx.x * 8 + warp) * 8;
         o[0] = t_start; o[1] = t_issued; o[2] = t_staged; o[3] = clock64(); o[4] = b1 - b0; o[5] = q - partRow[gpart];
     }
@@ -1407,6 +1407,23 @@ __global__ void rk4_taylor_kernel(long long N, double* __restrict__ u, const dou
         s = fma(c2, v2[i], s);
         s = fma(c1, v1[i], s);
         u[i] += s;
+    }
+}
+
+__global__ void rk4_taylor_cells_kernel(const int* __restrict__ cells, long long ncells, int KDp, double* __restrict__ u,
+                                        const double* __restrict__ v1, const double* __restrict__ v2,
+                                        const double* __restrict__ v3, const double* __restrict__ v4, double c1,
+                                        double c2, double c3, double c4) {
+    for (long long ci = blockIdx.x; ci < ncells; ci += gridDim.x) {
+        const long long base = (long long)cells[ci] * KDp;
+        for (int e = threadIdx.x; e < KDp; e += blockDim.x) {
+            const long long i = base + e;
+            double s = c4 * v4[i];
+            s = fma(c3, v3[i], s);
+            s = fma(c2, v2[i], s);
+            s = fma(c1, v1[i], s);
+            u[i] += s;
+        }
     }
 }
 

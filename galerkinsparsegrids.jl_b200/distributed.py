@@ -110,3 +110,173 @@ class ShardedRK4:
             self._rhs()
             o.rk_final(self.u_sh, self.k_sh, self.acc_sh, dt / 6.0)
             self._all_gather(self.u_sh)
+
+
+# ================================================================================================
+# Block-partitioned scheme (the one bench.py uses for N > 1)
+# ================================================================================================
+# nranks = 2^b.  Dimension D-j (j < b) splits the multi-level blocks into {level == 0} (rank bit j = 1)
+# and {level >= 1} (bit 0): every block has exactly one owner, the shares are balanced to ~10 % at
+# D=6, n=8 (50.5/49.5 at 2 ranks), and ownership depends on levels only, so
+#   * a sweep along a non-partition dimension is entirely local (every pole of an owned block is owned);
+#   * along a partition dimension d the poles with p >= 1 straddle exactly one rank pair.  The bit-0 rank
+#     (which holds all their level >= 1 cells) sweeps them: its partner sends the level_d == 0 blocks of
+#     the stage input before the sweep and receives the sweep's contribution to those blocks after it.
+# So one right-hand side costs 2 point-to-point messages per partition dimension per rank pair -- no
+# all-gather of the state -- and D-b of the D directions need no communication at all.
+# Vectors are full length on every rank (the device layout is global); a rank only reads and writes
+# the cells it owns plus the exchanged level-0 blocks.
+
+class ThreadComm:
+    """In-process stand-in for torch.distributed point-to-point (tests: one thread per virtual rank)."""
+
+    def __init__(self, world):
+        import queue
+        self.q = {(s, d): queue.Queue() for s in range(world) for d in range(world)}
+
+    def endpoint(self, rank):
+        comm = self
+
+        class _EP:
+            def send(self, t, dst):
+                comm.q[(rank, dst)].put(t.clone())
+
+            def recv(self, t, src):
+                t.copy_(comm.q[(src, rank)].get(timeout=120))
+
+            def exchange(self, sends, recvs):
+                for t, dst in sends:
+                    self.send(t, dst)
+                for t, src in recvs:
+                    self.recv(t, src)
+
+            def start(self, sends, recvs):
+                for t, dst in sends:
+                    self.send(t, dst)
+                return lambda: [self.recv(t, src) for t, src in recvs]
+
+        return _EP()
+
+
+class DistComm:
+    """torch.distributed point-to-point (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def exchange(self, sends, recvs):
+        ops = [dist.P2POp(dist.isend, t, dst, self.group) for t, dst in sends]
+        ops += [dist.P2POp(dist.irecv, t, src, self.group) for t, src in recvs]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def start(self, sends, recvs):
+        """post the messages now, return a callable that waits for them (NCCL: the transfer runs on the
+        communicator's stream beside whatever is launched in between)"""
+        ops = [dist.P2POp(dist.isend, t, dst, self.group) for t, dst in sends]
+        ops += [dist.P2POp(dist.irecv, t, src, self.group) for t, src in recvs]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        return lambda: [r.wait() for r in reqs]
+
+
+class PartitionedRK4:
+    """RK4 of u' = -sum_d a_d D_d u on a block-partitioned plan (Taylor form)."""
+
+    def __init__(self, plan, a, rank: int, world: int, device, comm):
+        self.plan, self.a, self.rank, self.world, self.comm = plan, [float(x) for x in a], rank, world, comm
+        self.device = device
+        plan.set_partition(rank, world)
+        self.D = plan.D
+        self.cs = plan.cell_stride
+        self.bits = max(world.bit_length() - 1, 0)
+
+        def cells_of(offs, sizes):
+            parts = [torch.arange(o // self.cs, (o + s) // self.cs, dtype=torch.int64) for o, s in zip(offs, sizes)]
+            return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64)
+
+        offs, sizes, _ = plan.partition_blocks(0)
+        self.owned = cells_of(offs, sizes).to(device)
+        self.owned_i32 = self.owned.to(torch.int32)
+        self.owned_doubles = int(sizes.sum())
+        self.ex = {}                      # partition dimension d -> (cells, partner, my bit)
+        for j in range(self.bits):
+            d = self.D - j
+            offs, sizes, partner = plan.partition_blocks(1, d)
+            self.ex[d] = (cells_of(offs, sizes).to(device), partner, (rank >> j) & 1)
+        n = plan.dev_size
+        self.v = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(5)]   # u, v1..v4
+        self.exchange_bytes_per_rhs = sum(2 * 8 * self.cs * c.numel() for c, _, _ in self.ex.values())
+
+    def _2d(self, t):
+        return t.view(-1, self.cs)
+
+    def set_state(self, full):
+        """full: the whole state in device layout (every rank passes the same vector)."""
+        self.v[0].zero_()
+        self._2d(self.v[0]).index_copy_(0, self.owned, self._2d(full).index_select(0, self.owned))
+
+    def owned_state(self):
+        """this rank's part of the state, zero elsewhere (sum over ranks = the full state)."""
+        out = torch.zeros_like(self.v[0])
+        self._2d(out).index_copy_(0, self.owned, self._2d(self.v[0]).index_select(0, self.owned))
+        return out
+
+    def rhs(self, w, k):
+        """k[owned] = -sum_d a_d D_d w   (w valid on the owned cells)."""
+        plan = self.plan
+        # 1. level-0 blocks of the stage input travel to the rank that sweeps the straddling poles
+        sends, recvs, staged = [], [], {}
+        for d, (cells, partner, bit) in self.ex.items():
+            if cells.numel() == 0 or self.a[d - 1] == 0.0:
+                continue
+            if bit == 1:
+                sends.append((self._2d(w).index_select(0, cells), partner))
+            else:
+                staged[d] = torch.empty(cells.numel(), self.cs, dtype=torch.float64, device=self.device)
+                recvs.append((staged[d], partner))
+        wait = self.comm.start(sends, recvs)
+        # 2. sweeps: the local directions run while the messages are in flight (the first one initialises k
+        #    on the owned cells); then the partition dimensions
+        first = True
+        local = [d for d in range(1, self.D + 1) if d not in self.ex]
+        for d in local:
+            ad = self.a[d - 1]
+            if ad == 0.0 and not first:
+                continue
+            plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
+            first = False
+        wait()
+        for d, buf in staged.items():
+            cells = self.ex[d][0]
+            self._2d(w).index_copy_(0, cells, buf)
+            self._2d(k).index_fill_(0, cells, 0.0)      # scratch for the partner's contribution
+        for d in sorted(self.ex):
+            ad = self.a[d - 1]
+            if ad == 0.0 and not first:
+                continue
+            plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
+            first = False
+        # 3. contributions to the partner's level-0 blocks travel back and are accumulated there
+        sends, recvs, back = [], [], {}
+        for d, (cells, partner, bit) in self.ex.items():
+            if cells.numel() == 0 or self.a[d - 1] == 0.0:
+                continue
+            if bit == 0:
+                sends.append((self._2d(k).index_select(0, cells), partner))
+            else:
+                back[d] = torch.empty(cells.numel(), self.cs, dtype=torch.float64, device=self.device)
+                recvs.append((back[d], partner))
+        self.comm.exchange(sends, recvs)
+        for d, buf in back.items():
+            self._2d(k).index_add_(0, self.ex[d][0], buf)
+
+    def step(self, dt: float, nsteps: int = 1):
+        u, v1, v2, v3, v4 = self.v
+        for _ in range(nsteps):
+            self.rhs(u, v1)
+            self.rhs(v1, v2)
+            self.rhs(v2, v3)
+            self.rhs(v3, v4)
+            self.plan.rk4_taylor_cells_dev(self.owned_i32, u, v1, v2, v3, v4, dt, dt * dt / 2.0, dt ** 3 / 6.0,
+                                           dt ** 4 / 24.0)

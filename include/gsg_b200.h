@@ -123,6 +123,23 @@ int gsg_rk4_wave_dev(gsg_plan* plan, double* u_dev, double* v_dev, double dt, in
 int gsg_energy(gsg_plan* plan, const double* u, const double* udot, double* energy_out);
 
 /* ---- building blocks for host-driven / multi-GPU time stepping (device layout) ------------ */
+/* ---- multi-GPU block partition -------------------------------------------
+ * nranks = 2^b ranks; dimension D-j (j < b) splits the multi-level blocks into {level == 0} (rank bit j
+ * = 1) and {level >= 1} (bit 0).  After this call the plan's sweeps cover only the pole groups this rank
+ * computes: directions 1..D-b are local; along a partition dimension the poles that straddle a rank pair
+ * are swept by the bit-0 rank once it has received the pair's level-0 blocks (list kind 1), and that
+ * rank returns its contribution for those blocks.  Vectors stay full-length (device layout). */
+int gsg_plan_set_partition(gsg_plan* plan, int rank, int nranks);
+/* kind 0: blocks owned by this rank; kind 1: level_d == 0 blocks exchanged with *partner_out along the
+ * partition dimension d (1-based; count 0 if d is not one).  Offsets/sizes in doubles of the device layout;
+ * call with offsets == NULL for the count. */
+int gsg_plan_partition_blocks(gsg_plan* plan, int kind, int d, int64_t* offsets, int64_t* sizes, int64_t* count,
+                              int* partner_out);
+/* u += c1 v1 + c2 v2 + c3 v3 + c4 v4 on the listed multi-cells (indices in units of the padded cell) */
+int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncells, double* u, const double* v1,
+                             const double* v2, const double* v3, const double* v4, double c1, double c2, double c3,
+                             double c4);
+
 /* Multi-GPU work sharing: after set_shard(rank, nranks) every sweep of this plan launches only
  * this rank's contiguous slice of each tile list, i.e. it ACCUMULATES a partial operator result
  * (the slices of all ranks sum to the full result; use beta = 1 into a zeroed vector). */

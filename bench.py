@@ -5,8 +5,11 @@
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
   python bench.py --impl reference ...                      the reference's CPU path (oracle port)
 
-One "step" = one classical RK4 step of the whole state = N_dof DOF-updates (4 right-hand sides,
-each D directional operator applies + the stage update).  Prints ONE JSON line (rank 0).
+One "step" = one classical RK4 step of the whole state = N_dof DOF-updates: 4 right-hand sides, each D
+directional operator applies.  The right-hand side is linear and time-independent, so the library advances
+the step in the Taylor form of RK4 (u += dt L u + dt^2/2 L^2 u + dt^3/6 L^3 u + dt^4/24 L^4 u: the same four
+operator applications, one combine pass instead of four stage updates); the staged
+form is timed beside it and reported as `staged_ms_per_step`.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -40,24 +43,85 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region, in-process through NVML (a thread
+    polling every 100 ms).  An external `nvidia-smi -lms 50` loop was measured to stall the GPU for ~11 ms
+    per query (4.7 vs 2.7 ms per step at 4 GPUs), so nvidia-smi is only the fallback, at -lms 500."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.proc = gpu_index, None
+        self.gpu, self.proc, self.thread, self.stop_flag = gpu_index, None, None, False
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
+
+    def _nvml_loop(self, pynvml, handle):
+        bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown")
+                else pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(handle))
+                    for name, bit in bits.items():
+                        if bit and (r & bit):
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def start(self):
+        if os.environ.get("GSG_NO_SAMPLER"):
+            return
         try:
+            import threading
+
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id when torch is available
+            handle = None
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        handle = h
+                        break
+            except Exception:
+                handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.how = "nvml thread, 100 ms"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.how = "nvidia-smi -lms 500"
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "500", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(self.sm),
+                    "reasons": sorted(self.reasons), "how": self.how}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -79,7 +143,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": self.how}
 
 
 def synthetic_state(g, D, k, n):
@@ -193,7 +257,9 @@ def main():
     run(W)
     barrier()
     sampler = ClockSampler(local_rank)
-    plan.profile_enable(True)
+    # CUDA events around the dominant kernel for a bounded sample of the timed region's launches (the first
+    # ~6 steps' worth: timing all of them costs ~8 % of the step)
+    plan.profile_enable(0 if os.environ.get("GSG_NO_PROFILE_EVENTS") else 144)
     l0 = g.launch_count()
     sampler.start()
     barrier()
@@ -209,6 +275,10 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if world > 1 and os.environ.get("GSG_PART_TIMING"):
+        rep = drv.timing_report()
+        print(f"[rank {rank}] owned {100.0 * drv.owned_doubles / plan.dev_size:.1f}% phases (device ms, host ms): "
+              + "; ".join(f"{k_}: {v_[0]:.3f}/{v_[1]:.3f} mean {v_[2]:.3f} max {v_[3]:.3f}" for k_, v_ in rep.items()), file=sys.stderr, flush=True)
     n_prof, prof_ms, prof_dofs = plan.profile_read()
     plan.profile_enable(False)
     value = N * K / (ms * 1e-3)
@@ -224,16 +294,16 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")   # from the committed ncu --set full capture
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("sweep_short_tma_kernel_bytes_per_launch")
+                traffic = json.load(open(tpath)).get("sweep_stream_kernel_bytes_per_launch")
             except Exception:
                 traffic = None
         roofline = {
-            "bound": "hbm", "kernel": "sweep_short_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "sweep_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_prof,
-            "kernel_share_of_step": prof_ms / ms,
+            "kernel_share_of_step": (prof_ms / n_prof) * (4 * D) / (ms / K),   # 4*D launches of it per step
             "note": ("16 B/DOF algorithmic; 5 of 6 launches per RHS accumulate (y += via TMA reduce-add), whose real "
-                     "HBM traffic is 24 B/DOF"),
+                     "HBM traffic is 24 B/DOF; timed: the first launches of the timed region (bounded sample)"),
             "step_model": {"bytes_per_dof_model": 64 * D + 144,
                            "achieved_gbs": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9,
                            "frac": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9 / peak},
@@ -260,6 +330,20 @@ def main():
         e2e = {"value": value, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "multi-GPU run: state resident (no host-buffer entry point for N>1 yet)"}
 
+    staged_ms = None
+    if world == 1:
+        plan.set_rk4_mode(1)
+        plan.rk4_advect_dev(a, y, DT, 2)
+        torch.cuda.synchronize(device)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks = max(4, K // 4)
+        s0.record(stream)
+        plan.rk4_advect_dev(a, y, DT, ks)
+        s1.record(stream)
+        torch.cuda.synchronize(device)
+        staged_ms = s0.elapsed_time(s1) / ks
+        plan.set_rk4_mode(0)
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(D, k, n, 1)
@@ -268,9 +352,10 @@ def main():
         line = {
             "metric": "RK4 DOF-updates/sec (D=%d sparse, k=%d, n=%d)" % (D, k, n),
             "value": value, "unit": "DOF-updates/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / K, "staged_ms_per_step": staged_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{D}-D sparse-grid advection u'=-sum_d D_d u, k={k} n={n} sparse, classical RK4, "
+            "config": {"workload": f"{D}-D sparse-grid advection u'=-sum_d D_d u, k={k} n={n} sparse, classical RK4 "
+                                   f"(Taylor form for the linear RHS: 4 operator applies + 1 combine pass), "
                                    f"N={N} DOFs (BASELINE config 4)",
                        "initial_condition": "prod_d sin(2 pi x_d) via tensor_construct", "dt": DT,
                        "l2": "inputs larger than L2 (4 state-sized vectors x %.0f MB vs 126 MB L2)" % (8e-6 * N),

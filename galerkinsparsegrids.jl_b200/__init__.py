@@ -358,8 +358,9 @@ class Plan:
     def rk_final_dev(self, length: int, u, k, acc, ca: float) -> None:
         check(lib.gsg_rk_final_dev(self._h, int(length), _devptr(u), _devptr(k), _devptr(acc), float(ca)))
 
-    def profile_enable(self, on: bool = True) -> None:
-        check(lib.gsg_profile_enable(self._h, 1 if on else 0))
+    def profile_enable(self, on=True) -> None:
+        """True: time every streaming-kernel launch; an int > 1: only the first `on` launches; False: off."""
+        check(lib.gsg_profile_enable(self._h, int(on)))
 
     def profile_read(self):
         """(launches, total_ms, dofs) of the timed streaming-kernel launches."""

@@ -188,7 +188,7 @@ struct gsg_plan {
     // optional timing of the dominant (streaming) kernel with CUDA events on its stream
     bool prof_on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
-    size_t prof_used = 0;
+    size_t prof_used = 0, prof_cap = 0;
     double prof_dofs = 0;         // DOFs processed by the profiled launches
 };
 
@@ -862,7 +862,7 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
         std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
         GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p, 0, sizeof(int), st));
-        const bool prof = pl.prof_on && pl.prof_used < pl.prof_ev.size();
+        const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         if (c.stream2) {
             auto kern2 = sweep_stream_kernel<K>;
@@ -1559,6 +1559,7 @@ int gsg_profile_enable(gsg_plan* plan, int on) {
         }
     }
     plan->prof_on = on != 0;
+    plan->prof_cap = on > 1 ? (size_t)on : plan->prof_ev.size();     // on > 1: time only the first `on` launches
     plan->prof_used = 0;
     plan->prof_dofs = 0;
     return 0;

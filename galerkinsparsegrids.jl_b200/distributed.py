@@ -206,6 +206,7 @@ class PartitionedRK4:
             self.ex[d] = (cells_of(offs, sizes).to(device), partner, (rank >> j) & 1)
         n = plan.dev_size
         self.v = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(5)]   # u, v1..v4
+        self.timing = [] if __import__("os").environ.get("GSG_PART_TIMING") else None
         self.exchange_bytes_per_rhs = sum(2 * 8 * self.cs * c.numel() for c, _, _ in self.ex.values())
 
     def _2d(self, t):
@@ -222,9 +223,30 @@ class PartitionedRK4:
         self._2d(out).index_copy_(0, self.owned, self._2d(self.v[0]).index_select(0, self.owned))
         return out
 
+    def _mark(self, name):
+        if self.timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timing.append((name, ev, __import__("time").perf_counter()))
+
+    def timing_report(self):
+        """average device / host milliseconds per phase of rhs() (development aid)"""
+        torch.cuda.synchronize()
+        import statistics
+        dev, host = {}, {}
+        for (n0, e0, t0), (n1, e1, t1) in zip(self.timing[:-1], self.timing[1:]):
+            if n1 == "begin":
+                continue
+            dev.setdefault(n1, []).append(e0.elapsed_time(e1))
+            host.setdefault(n1, []).append(1e3 * (t1 - t0))
+        half = {n: dev[n][len(dev[n]) // 2:] for n in dev}          # second half: past warm-up / connection setup
+        return {n: (statistics.median(dev[n]), statistics.median(host[n]), statistics.mean(half[n]), max(half[n]))
+                for n in dev}
+
     def rhs(self, w, k):
         """k[owned] = -sum_d a_d D_d w   (w valid on the owned cells)."""
         plan = self.plan
+        self._mark("begin")
         # 1. level-0 blocks of the stage input travel to the rank that sweeps the straddling poles
         sends, recvs, staged = [], [], {}
         for d, (cells, partner, bit) in self.ex.items():
@@ -236,6 +258,7 @@ class PartitionedRK4:
                 staged[d] = torch.empty(cells.numel(), self.cs, dtype=torch.float64, device=self.device)
                 recvs.append((staged[d], partner))
         wait = self.comm.start(sends, recvs)
+        self._mark("pack+post")
         # 2. sweeps: the local directions run while the messages are in flight (the first one initialises k
         #    on the owned cells); then the partition dimensions
         first = True
@@ -246,7 +269,9 @@ class PartitionedRK4:
                 continue
             plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
             first = False
+        self._mark("local sweeps")
         wait()
+        self._mark("wait recv")
         for d, buf in staged.items():
             cells = self.ex[d][0]
             self._2d(w).index_copy_(0, cells, buf)
@@ -257,6 +282,7 @@ class PartitionedRK4:
                 continue
             plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
             first = False
+        self._mark("unpack+partition sweeps")
         # 3. contributions to the partner's level-0 blocks travel back and are accumulated there
         sends, recvs, back = [], [], {}
         for d, (cells, partner, bit) in self.ex.items():
@@ -270,6 +296,7 @@ class PartitionedRK4:
         self.comm.exchange(sends, recvs)
         for d, buf in back.items():
             self._2d(k).index_add_(0, self.ex[d][0], buf)
+        self._mark("return exchange")
 
     def step(self, dt: float, nsteps: int = 1):
         u, v1, v2, v3, v4 = self.v

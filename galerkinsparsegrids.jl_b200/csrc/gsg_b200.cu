@@ -1772,6 +1772,28 @@ int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double*
     T.KDp = (int)pl.S.kDp;
     T.legw = 2 * (gsg::K_MAX + 1);
     const int nwarp = 8;
+    // second-generation kernel: factored mode products (low / high half of the dimensions)
+    if (!getenv("GSG_RECON_V1")) {
+        const int nlow = (T.D + 1) / 2;
+        long long KL = 1, KH = 1;
+        for (int d = 0; d < nlow; ++d) KL *= T.k;
+        for (int d = nlow; d < T.D; ++d) KH *= T.k;
+        const int n1 = T.n + 1, ntab = T.D * n1 * T.k;
+        const size_t lohi_bytes = ((size_t)T.KD * 4 + 15) & ~(size_t)15;
+        const size_t pw = ((size_t)T.nblocks * 8 + (size_t)(ntab + KL + KH) * 8 + (size_t)T.D * n1 * 4 + 15) & ~(size_t)15;
+        const size_t smem2 = lohi_bytes + pw * nwarp;
+        if (KL < 65536 && KH < 65536 && smem2 <= 200 * 1024) {
+            static thread_local size_t configured2 = 0;
+            GSG_TRY(ensure_smem(reconstruct2_kernel, smem2, configured2));
+            const int64_t want2 = (npts + nwarp - 1) / nwarp;
+            const int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>(want2, (int64_t)pl.sm_count * 8));
+            reconstruct2_kernel<<<grid2, nwarp * 32, smem2, pl.stream>>>(T, vcoeffs_dev, points_dev, npts, out_dev, (int)KL,
+                                                                          (int)KH, nlow);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GSG_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const size_t per_warp = ((size_t)T.D * (T.n + 1) * T.k + (size_t)T.D * (T.n + 1)) * sizeof(double);
     const size_t smem = per_warp * nwarp;
     if (smem > 200 * 1024) return fail(GSG_ERR_UNSUPPORTED, "reconstruct tables exceed shared memory");

@@ -1535,6 +1535,91 @@ reconstruct_kernel(ReconTables T, const double* __restrict__ coeffs, const doubl
     }
 }
 
+// Second-generation reconstruct kernel (the shipped path): still one warp per point, but the per-mode
+// product  prod_i v_i[m_i]  is factored into a LOW half (dims < nlow) and a HIGH half, each tabulated once per
+// (point, multi-level) by the warp (KL + KH products instead of D multiplications, divisions and table
+// look-ups for every one of the k^D coefficients), the element -> (low, high) index split is tabulated once
+// per CTA, and the cell offsets of all multi-levels are computed by the lanes in parallel.
+// ~70 instead of ~480 instructions per multi-level and lane at D=4, k=4: 1.5 M -> see DESIGN.md 4.7.
+__global__ void __launch_bounds__(256)
+reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const double* __restrict__ pts,
+                    long long npts, double* __restrict__ out, int KL, int KH, int nlow) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int D = T.D, k = T.k, n1 = T.n + 1;
+    const int ntab = D * n1 * k;
+    // per CTA: lohi[KD]; per warp: boff[nblocks] (8 B), bt[ntab], plh[KL+KH], ci[D*n1]
+    unsigned* lohi = reinterpret_cast<unsigned*>(rsm);
+    const size_t lohi_bytes = ((size_t)T.KD * 4 + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)T.nblocks * 8 + (size_t)(ntab + KL + KH) * 8 + (size_t)D * n1 * 4 + 15) & ~(size_t)15;
+    unsigned char* wb = rsm + lohi_bytes + (size_t)warp * per_warp;
+    long long* boff = reinterpret_cast<long long*>(wb);
+    double* bt = reinterpret_cast<double*>(wb + (size_t)T.nblocks * 8);
+    double* plh = bt + ntab;
+    int* ci = reinterpret_cast<int*>(plh + KL + KH);
+    const double sqrt2 = sqrt(2.0);
+
+    for (int e = threadIdx.x; e < T.KD; e += blockDim.x) lohi[e] = (unsigned)(e % KL) | ((unsigned)(e / KL) << 16);
+    __syncthreads();
+
+    for (long long pt = (long long)blockIdx.x * nwarp + warp; pt < npts; pt += (long long)gridDim.x * nwarp) {
+        __syncwarp();
+        for (int idx = lane; idx < ntab; idx += 32) {
+            const int m = idx % k, dl = idx / k, l = dl % n1, d = dl / n1;
+            const double x = pts[pt * D + d];
+            long long cell;   // 1-based, src/dg_methods.jl:70-79
+            if (l <= 1) cell = 1;
+            else if (x >= 1.0) cell = 1LL << (l - 1);
+            else cell = 1 + (long long)floor((double)(1LL << (l - 1)) * x);
+            double val;
+            if (l == 0) {
+                val = poly_eval(T.leg + m * T.legw, T.legw / 2, 2.0 * x - 1.0) * sqrt2;
+            } else {
+                const double sc = (double)(1LL << l);
+                val = poly_eval(T.dg + m * 2 * k, k, sc * x - (double)(2 * cell - 1)) * sqrt(sc);
+            }
+            bt[idx] = val;
+            if (m == 0) ci[dl] = (int)(cell - 1);
+        }
+        __syncwarp();
+        for (int b = lane; b < T.nblocks; b += 32) {          // cell offsets of all multi-levels
+            const unsigned char* lv = T.blk_level + (size_t)b * D;
+            long long lin = 0, stride = 1;
+            for (int d = 0; d < D; ++d) {
+                const int l = lv[d];
+                lin += (long long)ci[d * n1 + l] * stride;
+                stride *= (l <= 1) ? 1 : (1LL << (l - 1));
+            }
+            boff[b] = T.blk_offset[b] + lin * T.KDp;
+        }
+        __syncwarp();
+        double acc = 0.0;
+        for (int b = 0; b < T.nblocks; ++b) {
+            const unsigned char* lv = T.blk_level + (size_t)b * D;
+            for (int j = lane; j < KL + KH; j += 32) {
+                int rem = j < KL ? j : j - KL;
+                const int d0 = j < KL ? 0 : nlow, d1 = j < KL ? nlow : D;
+                double prod = 1.0;
+                for (int d = d0; d < d1; ++d) {
+                    const int m = rem % k;
+                    rem /= k;
+                    prod *= bt[(d * n1 + lv[d]) * k + m];
+                }
+                plh[j] = prod;
+            }
+            __syncwarp();
+            const double* cf = coeffs + boff[b];
+            for (int e = lane; e < T.KD; e += 32) {
+                const unsigned u = lohi[e];
+                acc = fma(cf[e], plh[u & 0xffffu] * plh[KL + (u >> 16)], acc);
+            }
+            __syncwarp();
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[pt] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // CSR SpMV cross-check: LANES lanes per row, int32 columns.
 // ------------------------------------------------------------------------------------------

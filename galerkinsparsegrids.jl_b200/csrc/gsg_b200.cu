@@ -820,7 +820,8 @@ inline void tile_range(const gsg_plan& pl, int ntiles, int& begin, int& count) {
 
 int launch_check(const char* what, int K, const SweepClass& c) {
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && getenv("GSG_DEBUG_SYNC")) e = cudaDeviceSynchronize();
+    static const bool debug_sync = getenv("GSG_DEBUG_SYNC") != nullptr;
+    if (e == cudaSuccess && debug_sync) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof buf, "%s<K=%d> p=%d ntiles=%d smem=%zu NPOLE=%d Amin=%d: %s", what, K, c.p, c.ntiles,
@@ -1054,7 +1055,8 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
         g_launches.fetch_add(1, std::memory_order_relaxed);
         beta = 1.0;
     }
-    const bool fork = nc > 1 && !getenv("GSG_NO_FORK");
+    static const bool no_fork = getenv("GSG_NO_FORK") != nullptr;
+    const bool fork = nc > 1 && !no_fork;
     if (fork) {
         GSG_CUDA(cudaEventRecord(pl.ev_fork, pl.stream));
         for (size_t i = 1; i < nc; ++i) GSG_CUDA(cudaStreamWaitEvent(pl.aux[i], pl.ev_fork, 0));
@@ -1781,8 +1783,10 @@ int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double*
         const int n1 = T.n + 1, ntab = T.D * n1 * T.k;
         const size_t lohi_bytes = ((size_t)T.KD * 4 + 15) & ~(size_t)15;
         const size_t pw = ((size_t)T.nblocks * 8 + (size_t)(ntab + KL + KH) * 8 + (size_t)T.D * n1 * 4 + 15) & ~(size_t)15;
-        const size_t smem2 = lohi_bytes + pw * nwarp;
-        if (KL < 65536 && KH < 65536 && smem2 <= 200 * 1024) {
+        const size_t pdig_bytes = ((size_t)(KL + KH) * 4 + 15) & ~(size_t)15;
+        const size_t lvl_bytes = ((size_t)T.nblocks * T.D + 15) & ~(size_t)15;
+        const size_t smem2 = lohi_bytes + pdig_bytes + lvl_bytes + pw * nwarp;
+        if (KL < 65536 && KH < 65536 && nlow <= 6 && smem2 <= 200 * 1024) {
             static thread_local size_t configured2 = 0;
             GSG_TRY(ensure_smem(reconstruct2_kernel, smem2, configured2));
             const int64_t want2 = (npts + nwarp - 1) / nwarp;

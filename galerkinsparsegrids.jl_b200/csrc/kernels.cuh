@@ -1548,18 +1548,33 @@ reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const doub
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int D = T.D, k = T.k, n1 = T.n + 1;
     const int ntab = D * n1 * k;
-    // per CTA: lohi[KD]; per warp: boff[nblocks] (8 B), bt[ntab], plh[KL+KH], ci[D*n1]
+    const int KLH = KL + KH;
+    // per CTA: lohi[KD] (element -> low / high product index), pdig[KL+KH] (product index -> packed mode
+    // digits), lvl[nblocks*D] (block levels); per warp: boff[nblocks] (8 B), bt[ntab], plh[KL+KH], ci[D*n1]
     unsigned* lohi = reinterpret_cast<unsigned*>(rsm);
     const size_t lohi_bytes = ((size_t)T.KD * 4 + 15) & ~(size_t)15;
-    const size_t per_warp = ((size_t)T.nblocks * 8 + (size_t)(ntab + KL + KH) * 8 + (size_t)D * n1 * 4 + 15) & ~(size_t)15;
-    unsigned char* wb = rsm + lohi_bytes + (size_t)warp * per_warp;
+    unsigned* pdig = reinterpret_cast<unsigned*>(rsm + lohi_bytes);
+    const size_t pdig_bytes = ((size_t)KLH * 4 + 15) & ~(size_t)15;
+    unsigned char* lvl = rsm + lohi_bytes + pdig_bytes;
+    const size_t lvl_bytes = ((size_t)T.nblocks * D + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)T.nblocks * 8 + (size_t)(ntab + KLH) * 8 + (size_t)D * n1 * 4 + 15) & ~(size_t)15;
+    unsigned char* wb = rsm + lohi_bytes + pdig_bytes + lvl_bytes + (size_t)warp * per_warp;
     long long* boff = reinterpret_cast<long long*>(wb);
     double* bt = reinterpret_cast<double*>(wb + (size_t)T.nblocks * 8);
     double* plh = bt + ntab;
-    int* ci = reinterpret_cast<int*>(plh + KL + KH);
+    int* ci = reinterpret_cast<int*>(plh + KLH);
     const double sqrt2 = sqrt(2.0);
+    const int nhigh = D - nlow;
 
     for (int e = threadIdx.x; e < T.KD; e += blockDim.x) lohi[e] = (unsigned)(e % KL) | ((unsigned)(e / KL) << 16);
+    for (int j = threadIdx.x; j < KLH; j += blockDim.x) {       // up to 6 digits of 4 bits (k <= 10, D <= 12)
+        int rem = j < KL ? j : j - KL;
+        const int nd = j < KL ? nlow : nhigh;
+        unsigned pk = 0;
+        for (int d = 0; d < nd; ++d) { pk |= (unsigned)(rem % k) << (4 * d); rem /= k; }
+        pdig[j] = pk;
+    }
+    for (int i = threadIdx.x; i < T.nblocks * D; i += blockDim.x) lvl[i] = T.blk_level[i];
     __syncthreads();
 
     for (long long pt = (long long)blockIdx.x * nwarp + warp; pt < npts; pt += (long long)gridDim.x * nwarp) {
@@ -1583,7 +1598,7 @@ reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const doub
         }
         __syncwarp();
         for (int b = lane; b < T.nblocks; b += 32) {          // cell offsets of all multi-levels
-            const unsigned char* lv = T.blk_level + (size_t)b * D;
+            const unsigned char* lv = lvl + (size_t)b * D;
             long long lin = 0, stride = 1;
             for (int d = 0; d < D; ++d) {
                 const int l = lv[d];
@@ -1595,15 +1610,14 @@ reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const doub
         __syncwarp();
         double acc = 0.0;
         for (int b = 0; b < T.nblocks; ++b) {
-            const unsigned char* lv = T.blk_level + (size_t)b * D;
-            for (int j = lane; j < KL + KH; j += 32) {
-                int rem = j < KL ? j : j - KL;
+            const unsigned char* lv = lvl + (size_t)b * D;
+            for (int j = lane; j < KLH; j += 32) {
+                unsigned pk = pdig[j];
                 const int d0 = j < KL ? 0 : nlow, d1 = j < KL ? nlow : D;
                 double prod = 1.0;
                 for (int d = d0; d < d1; ++d) {
-                    const int m = rem % k;
-                    rem /= k;
-                    prod *= bt[(d * n1 + lv[d]) * k + m];
+                    prod *= bt[(d * n1 + lv[d]) * k + (pk & 15u)];
+                    pk >>= 4;
                 }
                 plh[j] = prod;
             }

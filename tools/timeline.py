@@ -10,6 +10,9 @@ plan = g.Plan(D, k, n)
 v1 = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
 x = plan.to_device(g.tensor_construct(D, k, n, [v1] * D))
 y = torch.zeros_like(x)
+if os.environ.get("GSG_PART"):
+    r_, w_ = [int(t) for t in os.environ["GSG_PART"].split(",")]
+    plan.set_partition(r_, w_)
 lib.gsg_debug_stamps.restype = C.c_int
 lib.gsg_debug_stamps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 for _ in range(3):

@@ -263,3 +263,71 @@ def test_block_partition_matches_single_gpu(oracle, world):
     # ownership is a partition: every cell owned exactly once is implied by the sum matching;
     # and no rank owns everything
     assert all(float(o.abs().sum()) > 0 for o in outs)
+
+
+def _sample_pole_indices(oracle, D, d, k, n, rng, npoles):
+    """Global (reference-layout) indices of `npoles` random poles along axis d, each in 1-D layout order
+    (level, cell, mode), computed from the block table alone (src/dg_vmethods.jl:53-73 strides)."""
+    blocks, N = oracle.block_table(D, k, n)
+    by_level = {lv: (off, ks) for lv, off, ks in blocks}
+    starts = [lv for lv, _, _ in blocks if lv[d - 1] == 0]
+    kD = k ** D
+    out = []
+    for _ in range(npoles):
+        lv0 = starts[rng.integers(len(starts))]
+        p = n - sum(lv0)
+        ks0 = by_level[lv0][1]
+        cells = [int(rng.integers(ks0[j])) for j in range(D)]
+        modes = [int(rng.integers(k)) for j in range(D)]
+        idx = []
+        for ld in range(p + 1):
+            lv = lv0[:d - 1] + (ld,) + lv0[d:]
+            off, ks = by_level[lv]
+            cstr = [kD * int(np.prod(ks[:j], dtype=np.int64)) for j in range(D)]
+            base = off + sum(cells[j] * cstr[j] + modes[j] * k ** j for j in range(D) if j != d - 1)
+            for c in range(ks[d - 1]):
+                for m in range(k):
+                    idx.append(base + c * cstr[d - 1] + m * k ** (d - 1))
+        out.append(np.array(idx, dtype=np.int64))
+    return out
+
+
+def test_full_size_baseline_config(gsg, oracle):
+    """BASELINE config 4 at full size (D=6, k=3, n=8, 34.5 M DOFs): sampled poles of every direction against
+    the oracle's H (every pole-length class, N' = 3 ... 768), linearity, skew-symmetry."""
+    import scipy.sparse as sp
+    D, k, n = 6, 3, 8
+    H = gsg.periodic_DLF_matrix(k, n)                 # the library's own H (test_abi pins it to the oracle's)
+    plan = gsg.Plan(D, k, n, "sparse", H=H)
+    assert plan.size == 34455456
+    Hd = sp.csr_matrix(H)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(plan.size)
+    y = rng.standard_normal(plan.size)
+    for d in range(1, D + 1):
+        Dx = plan.apply_D(d, x)
+        worst, lengths = 0.0, set()
+        for idx in _sample_pole_indices(oracle, D, d, k, n, rng, 120):
+            Np = idx.size
+            lengths.add(Np)
+            ref = Hd[:Np, :Np] @ x[idx]
+            worst = max(worst, float(np.abs(Dx[idx] - ref).max() / np.abs(ref).max()))
+        assert worst <= 1e-12, (d, worst)
+        assert len(lengths) >= 5                      # several pole-length classes were hit
+        if d in (1, 6):
+            Dy = plan.apply_D(d, y)
+            assert relerr(plan.apply_D(d, 2.0 * x - 3.0 * y), 2.0 * Dx - 3.0 * Dy) <= 1e-13
+            skew = abs(np.dot(x, Dy) + np.dot(Dx, y)) / (np.linalg.norm(x) * np.linalg.norm(Dy))
+            assert skew < 1e-9
+    # the two RK4 drivers (Taylor form / staged form) agree at full size, and the state moves
+    a = np.ones(D)
+    u0 = gsg.tensor_construct(D, k, n, [gsg.vcoeffs_DG(1, k, n, f_sin)] * D)
+    u_taylor = plan.rk4_advect(a, u0, 1.0e-4, 3)
+    plan.set_rk4_mode(1)
+    u_staged = plan.rk4_advect(a, u0, 1.0e-4, 3)
+    plan.set_rk4_mode(0)
+    assert relerr(u_taylor, u_staged) <= 1e-12
+    assert relerr(u_taylor, u0) > 1e-4
+    # advection by a = (1,...,1) of prod sin(2 pi x_d) conserves the L2 norm to time-stepping accuracy
+    assert abs(np.linalg.norm(u_taylor) / np.linalg.norm(u0) - 1.0) < 1e-6
+    del plan

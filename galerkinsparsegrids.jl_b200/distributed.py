@@ -207,6 +207,8 @@ class PartitionedRK4:
         n = plan.dev_size
         self.v = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(5)]   # u, v1..v4
         self.timing = [] if __import__("os").environ.get("GSG_PART_TIMING") else None
+        self.use_graphs = bool(__import__("os").environ.get("GSG_PART_GRAPH")) and torch.device(device).type == "cuda"
+        self.graphs, self.graph_seen, self.recv_bufs = {}, {}, {}
         self.exchange_bytes_per_rhs = sum(2 * 8 * self.cs * c.numel() for c, _, _ in self.ex.values())
 
     def _2d(self, t):
@@ -222,6 +224,30 @@ class PartitionedRK4:
         out = torch.zeros_like(self.v[0])
         self._2d(out).index_copy_(0, self.owned, self._2d(self.v[0]).index_select(0, self.owned))
         return out
+
+    def _run(self, tag, w, k, fn, staged=None):
+        """Run a group of sweeps: eagerly, or (GSG_PART_GRAPH=1, CUDA only) replayed from a CUDA graph captured
+        per (phase, input vector, output vector) -- a rank's sweeps are launch-latency-bound, a replay costs one
+        launch.  Receive buffers of a captured phase are persistent (the graph holds their addresses)."""
+        if not self.use_graphs:
+            fn()
+            return
+        key = (tag, w.data_ptr(), k.data_ptr())
+        ent = self.graphs.get(key)
+        if ent is None:
+            self.graph_seen[key] = self.graph_seen.get(key, 0) + 1
+            if self.graph_seen[key] < 2:          # first visit: eager (kernel attributes get configured)
+                fn()
+                return
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            with torch.cuda.graph(g):
+                self.plan.set_stream(torch.cuda.current_stream())
+                fn()
+            self.plan.set_stream(cur)
+            self.graphs[key] = g
+            ent = g
+        ent.replay()
 
     def _mark(self, name):
         if self.timing is not None:
@@ -255,33 +281,46 @@ class PartitionedRK4:
             if bit == 1:
                 sends.append((self._2d(w).index_select(0, cells), partner))
             else:
-                staged[d] = torch.empty(cells.numel(), self.cs, dtype=torch.float64, device=self.device)
+                bkey = (d, w.data_ptr())
+                if bkey not in self.recv_bufs:
+                    self.recv_bufs[bkey] = torch.empty(cells.numel(), self.cs, dtype=torch.float64, device=self.device)
+                staged[d] = self.recv_bufs[bkey]
                 recvs.append((staged[d], partner))
         wait = self.comm.start(sends, recvs)
         self._mark("pack+post")
         # 2. sweeps: the local directions run while the messages are in flight (the first one initialises k
         #    on the owned cells); then the partition dimensions
-        first = True
         local = [d for d in range(1, self.D + 1) if d not in self.ex]
-        for d in local:
-            ad = self.a[d - 1]
-            if ad == 0.0 and not first:
-                continue
-            plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
-            first = False
+        any_local = any(self.a[d - 1] != 0.0 for d in local) or not self.ex
+
+        def local_sweeps():
+            first = True
+            for d in local:
+                ad = self.a[d - 1]
+                if ad == 0.0 and not first:
+                    continue
+                plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
+                first = False
+
+        def partition_sweeps():
+            first = not any_local
+            for d, buf in staged.items():
+                cells = self.ex[d][0]
+                self._2d(w).index_copy_(0, cells, buf)
+                self._2d(k).index_fill_(0, cells, 0.0)      # scratch for the partner's contribution
+            for d in sorted(self.ex):
+                ad = self.a[d - 1]
+                if ad == 0.0 and not first:
+                    continue
+                plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
+                first = False
+
+        self._run("local", w, k, local_sweeps)
         self._mark("local sweeps")
         wait()
         self._mark("wait recv")
-        for d, buf in staged.items():
-            cells = self.ex[d][0]
-            self._2d(w).index_copy_(0, cells, buf)
-            self._2d(k).index_fill_(0, cells, 0.0)      # scratch for the partner's contribution
-        for d in sorted(self.ex):
-            ad = self.a[d - 1]
-            if ad == 0.0 and not first:
-                continue
-            plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
-            first = False
+        self._staged = staged
+        self._run("part", w, k, partition_sweeps, staged)
         self._mark("unpack+partition sweeps")
         # 3. contributions to the partner's level-0 blocks travel back and are accumulated there
         sends, recvs, back = [], [], {}

@@ -65,6 +65,14 @@ def device_info(device: int = 0) -> dict:
     return {"name": name, "sm_count": int(sms), "cc": cc, "global_mem": int(mem)}
 
 
+def block_pattern(n: int) -> np.ndarray:
+    """(2^n, 2^n) boolean structural block pattern of periodic_DLF_matrix(k, n) (include/gsg_b200.h)."""
+    nq = 1 << n
+    out = np.zeros((nq, nq), dtype=np.uint8)
+    check(lib.gsg_block_pattern(int(n), _ptr(out)))
+    return out.astype(bool)
+
+
 def get_size(D: int, k: int, n: int, scheme: str = "sparse") -> int:
     """get_size(Val(D), k, n, Val(scheme)) -- src/dg_vmethods.jl:35-45."""
     out = C.c_int64()

@@ -46,6 +46,7 @@ SIGNATURES = {
     "gsg_cell_index": (i32, [f64, i32, p_i64]),
     "gsg_basis_tables": (i32, [i32, vp, vp]),
     "gsg_dlf_matrix": (i32, [i32, i32, i32, p_i64, vp, vp, vp]),
+    "gsg_block_pattern": (i32, [i32, vp]),
     "gsg_tensor_construct": (i32, [i32, i32, i32, i32, C.POINTER(vp), vp]),
     "gsg_plan_create": (i32, [i32, i32, i32, i32, i64, vp, vp, vp, i32, C.POINTER(vp)]),
     "gsg_plan_destroy": (i32, [vp]),

@@ -831,8 +831,16 @@ int launch_check(const char* what, int K, const SweepClass& c) {
     return 0;
 }
 
+// Kernel attributes are per device: the per-kernel `configured` cache passed in by the launchers only
+// remembers the largest size set on the device that set it, so it is keyed by the current device here
+// (one process may hold plans on several GPUs).
 template <class Kern>
-int ensure_smem(Kern kern, size_t smem, size_t& configured) {
+int ensure_smem(Kern kern, size_t smem, size_t& configured_unused) {
+    (void)configured_unused;
+    static thread_local std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    GSG_CUDA(cudaGetDevice(&dev));
+    size_t& configured = done[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
     if (configured == 0) {
         // every sweep kernel asks for the maximum shared-memory carve-out: kernels with different
         // carve-outs cannot be resident on one SM at the same time
@@ -1324,6 +1332,17 @@ int gsg_tensor_construct(int D, int k, int n, int scheme, const double* const* v
     gsg::IndexSet S;
     S.build(D, k, n, scheme);
     gsg::tensor_construct(S, vcoeffs_1d, out);
+    return 0;
+}
+
+// structural block pattern of periodic_DLF_matrix(k, n) in the hierarchical basis: out[q * 2^n + r] = 1 iff
+// the closed supports of 1-D cells q and r intersect or touch periodically (what the constant-bank kernel
+// is unrolled for)
+int gsg_block_pattern(int n, unsigned char* out) {
+    if (n < 0 || n > gsg::N_MAX_LEVEL || !out) return fail(GSG_ERR_ARG, "bad argument");
+    const int nq = 1 << n;
+    for (int q = 0; q < nq; ++q)
+        for (int r = 0; r < nq; ++r) out[(size_t)q * nq + r] = pat::touch(q, r) ? 1 : 0;
     return 0;
 }
 

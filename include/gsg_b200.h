@@ -65,6 +65,10 @@ int gsg_basis_tables(int k, double* leg_out, double* dg_out);
  * two-call pattern: pass nzval == NULL to query nnz.  basis: 0 = hier, 1 = pos. */
 int gsg_dlf_matrix(int k, int n, int basis, int64_t* nnz_inout,
                    int64_t* colptr, int64_t* rowval, double* nzval);
+/* Structural block pattern of periodic_DLF_matrix(k, n) (src/1d_derivative.jl:113-117; k x k blocks indexed by
+ * the 1-D cells q = 0 (level 0), 2^(l-1) + c (level l >= 1)): out[q * 2^n + r] = 1 iff the closed supports of
+ * cells q and r intersect or touch periodically.  out has 4^n bytes. */
+int gsg_block_pattern(int n, unsigned char* out);
 /* tensor_construct(D, k, n, [v_1..v_D]; scheme) on 1-D coefficient vectors of length k*2^n,
  * result in vector layout                                     src/tensor_construct.jl:19-63 */
 int gsg_tensor_construct(int D, int k, int n, int scheme, const double* const* vcoeffs_1d,

@@ -93,3 +93,15 @@ def test_argument_errors(gsg):
         gsg.get_size(2, 11, 3)                           # k > K_max -> DomainError
     with pytest.raises(ValueError):
         gsg.periodic_DLF_matrix(3, 3, basis="nodal")     # broken in the reference as well
+
+
+@pytest.mark.parametrize("k,n", [(3, 6), (2, 5), (4, 4), (1, 5)])
+def test_structural_block_pattern_matches_oracle_H(gsg, oracle, k, n):
+    """The pattern the constant-bank kernel is unrolled for (supports intersect or touch periodically) is
+    exactly the stored k x k block pattern of the oracle's H = periodic_DLF_matrix(k, n)."""
+    H = oracle.periodic_DLF_matrix(k, n)
+    nq = 1 << n
+    stored = np.zeros((nq, nq), dtype=bool)
+    cols = np.repeat(np.arange(H.n), np.diff(H.colptr))
+    stored[np.asarray(H.rowval) // k, cols // k] = True
+    assert np.array_equal(gsg.block_pattern(n), stored)

@@ -155,11 +155,17 @@ struct gsg_plan {
     std::vector<std::vector<double>> consth_vals;
 
     std::vector<Direction> dirs;
+    // direction-pair fusion (streaming classes): pair j = dimensions (2j, 2j+1).  pair_np = largest n' of the
+    // 2-D sub-planes handled by PAIR tiles (-1 = off); dirs_red = the directions WITHOUT the pole groups those
+    // tiles cover (used only by the fused gradient / advection right-hand side)
+    int pair_np = -1;
+    std::vector<Direction> dirs_red;
+    std::vector<SweepClass> pairs;
 
     // fork/join streams so the launches of one sweep run concurrently
     std::vector<cudaStream_t> aux;
     std::vector<cudaEvent_t> ev_done;
-    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_pair_fork = nullptr, ev_pair_done = nullptr;
 
     // reconstruct tables
     DevBuf<unsigned char> r_level;
@@ -391,10 +397,9 @@ int get_col_passes(gsg_plan& P, int p, int npass, const std::vector<std::unique_
     return 0;
 }
 
-int build_direction(gsg_plan& P, int d /*0-based*/) {
+int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_np /* -1: keep every group */) {
     const gsg::IndexSet& S = P.S;
     const int D = S.D, K = S.k, n = S.n;
-    Direction& dir = P.dirs[d];
     dir.A = pow_int(K, d);
     const int KD = (int)S.kD, KDp = (int)S.kDp;
     const int PI = KD / K;
@@ -433,6 +438,13 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
             else mine = mine && ((b0.level[e] == 0) == (mybit == 1));
         }
         if (!mine) continue;
+        if (exclude_np >= 0) {            // groups covered by the PAIR tiles of this direction's pair
+            const int pa = d & ~1, pb = pa + 1;
+            int s_other = 0;
+            for (int i = 0; i < D; ++i)
+                if (i != pa && i != pb) s_other += b0.level[i];
+            if (n - s_other <= exclude_np) continue;
+        }
         groups.push_back(g);
     }
     GSG_TRY(dir.groups.upload(groups));
@@ -811,6 +823,127 @@ int build_direction(gsg_plan& P, int d /*0-based*/) {
     return 0;
 }
 
+// PAIR tiles (direction-pair fusion of the streaming classes, kernels.cuh): whole 2-D sub-planes with n' <= pair_np
+int build_pairs(gsg_plan& P) {
+    const gsg::IndexSet& S = P.S;
+    const int D = S.D, K = S.k, n = S.n;
+    P.pair_np = -1;
+    P.pairs.clear();
+    P.dirs_red.clear();
+    if (getenv("GSG_NO_PAIR") || S.scheme != 0 || D < 2 || K > 5 || P.short_pmax < 0 || P.part_bits > 0) return 0;
+    int npmax = K <= 3 ? 2 : (K == 4 ? 1 : 0);
+    npmax = std::min(npmax, std::min(P.short_pmax, n));
+    if (const char* e = getenv("GSG_PAIR_NP")) npmax = std::min(npmax, atoi(e));
+    if (npmax < 0) return 0;
+    const int KD = (int)S.kD, KDp = (int)S.kDp;
+    const int CT = 8;                                             // multi-cells per ring stage
+    if ((long long)CT * KDp * 8 * 2 > 200 * 1024) return 0;
+    const int npairs = D / 2;
+    P.pairs.resize(npairs);
+    for (int j = 0; j < npairs; ++j) {
+        const int da = 2 * j, db = da + 1;
+        SweepClass& c = P.pairs[j];
+        c.kind = Kind::SHORT_TMA;
+        c.stream2 = true;
+        std::vector<TileS2> tl;
+        for (int np = npmax; np >= 0; --np) {                     // largest sub-planes first
+            const int NC = pairp::ncell(np), nr_max = CT / NC;
+            // plane groups: levels of the other dims with n - sum == np; representative = the (0, 0) block
+            for (const gsg::Block& b0 : S.blocks) {
+                if (b0.level[da] != 0 || b0.level[db] != 0) continue;
+                int s_other = 0;
+                for (int i = 0; i < D; ++i) s_other += b0.level[i];
+                if (n - s_other != np) continue;
+                long long nitems = 1;
+                for (int i = 0; i < D; ++i)
+                    if (i != da && i != db) nitems *= b0.cells[i];
+                // per slot: block and the cell strides of the other dims inside it
+                std::vector<const gsg::Block*> sblk(NC);
+                std::vector<long long> sfix(NC);                  // cell offset contributed by (c_a, c_b)
+                for (int qb = 0; qb < (1 << np); ++qb)
+                    for (int qa = 0; qa < (1 << np); ++qa) {
+                        const int sidx = pairp::slot(np, qa, qb);
+                        if (sidx < 0) continue;
+                        std::vector<int> lv = b0.level;
+                        const int la = pairp::lvl(qa), lb = pairp::lvl(qb);
+                        lv[da] = la; lv[db] = lb;
+                        auto it = S.by_level.find(lv);
+                        if (it == S.by_level.end()) return fail(GSG_ERR_ARG, "internal: missing block (pair)");
+                        const gsg::Block& bk = S.blocks[it->second];
+                        const int ca = la <= 1 ? 0 : qa - (1 << (la - 1)), cb = lb <= 1 ? 0 : qb - (1 << (lb - 1));
+                        long long stride = 1, fix = 0;
+                        for (int i = 0; i < D; ++i) {
+                            if (i == da) fix += ca * stride;
+                            if (i == db) fix += cb * stride;
+                            stride *= bk.cells[i];
+                        }
+                        sblk[sidx] = &bk;
+                        sfix[sidx] = fix;
+                    }
+                for (long long r0 = 0; r0 < nitems; r0 += nr_max) {
+                    const int nr = (int)std::min<long long>(nr_max, nitems - r0);
+                    TileS2 o;
+                    std::memset(&o, 0, sizeof(o));
+                    o.P = (short)np;
+                    o.nr = (short)nr;
+                    o.ncell = NC * nr;
+                    int nruns = 0;
+                    for (int sidx = 0; sidx < NC; ++sidx) {
+                        const gsg::Block& bk = *sblk[sidx];
+                        long long prev = -2;
+                        for (int r = 0; r < nr; ++r) {
+                            // item index -> cells of the other dims (first other dim fastest) -> offset in this block
+                            long long rem = r0 + r, stride = 1, lin = sfix[sidx];
+                            for (int i = 0; i < D; ++i) {
+                                if (i != da && i != db) {
+                                    const long long ci = rem % b0.cells[i];
+                                    rem /= b0.cells[i];
+                                    lin += ci * stride;
+                                }
+                                stride *= bk.cells[i];
+                            }
+                            if (bk.poffset % KDp != 0) return fail(GSG_ERR_UNSUPPORTED, "internal: unaligned block");
+                            const long long cell = bk.poffset / KDp + lin;
+                            if (cell > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many multi-cells");
+                            if (cell == prev + 1 && nruns > 0) {
+                                ++o.run[nruns - 1].n;
+                            } else {
+                                if (nruns == TILE2_MAXRUN) return fail(GSG_ERR_UNSUPPORTED, "internal: too many runs");
+                                o.run[nruns].cell0 = (int)cell;
+                                o.run[nruns].scell = (short)(sidx * nr + r);
+                                o.run[nruns].n = 1;
+                                ++nruns;
+                            }
+                            prev = cell;
+                        }
+                    }
+                    o.nruns = nruns;
+                    tl.push_back(o);
+                    c.short_dofs += (double)NC * nr * KD;
+                }
+            }
+        }
+        c.ntiles = (int)tl.size();
+        if (c.ntiles == 0) { P.pairs.clear(); return 0; }
+        GSG_TRY(c.s2tiles.upload(tl));
+        const int PI = KD / K;
+        const size_t fixed = 128 + std::max(8 * sizeof(TileS), 4 * sizeof(TileS2)) + (size_t)PI * 4 + 128;
+        int ns = 4;
+        while (ns > 2 && fixed + (size_t)ns * CT * KDp * 8 > 200 * 1024) --ns;
+        c.sprm.KD = KD;
+        c.sprm.KDp = KDp;
+        c.sprm.A = pow_int(K, da);
+        c.sprm.stage_doubles = CT * KDp;
+        c.sprm.nstage = ns;
+        c.smem = fixed + (size_t)ns * CT * KDp * 8;
+        c.p = npmax;
+    }
+    P.pair_np = npmax;
+    P.dirs_red.resize(2 * npairs);
+    for (int d = 0; d < 2 * npairs; ++d) GSG_TRY(build_direction(P, d, P.dirs_red[d], npmax));
+    return 0;
+}
+
 // tile range of this process (multi-GPU work sharing)
 inline void tile_range(const gsg_plan& pl, int ntiles, int& begin, int& count) {
     begin = (int)((long long)ntiles * pl.shard_rank / pl.shard_n);
@@ -874,10 +1007,10 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         if (c.stream2) {
-            auto kern2 = sweep_stream_kernel<K>;
+            auto kern2 = sweep_stream_kernel<K, false>;
             static thread_local size_t configured2 = 0;
             GSG_TRY(ensure_smem(kern2, c.smem, configured2));
-            kern2<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, c.s2tiles.p + tb, tn, hd,
+            kern2<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha, 0.0, beta != 0.0 ? 1 : 0, c.s2tiles.p + tb, tn, hd,
                                                          c.sprm, pl.tile_counter.p, pl.dbg);
         } else
         kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
@@ -892,6 +1025,29 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         return launch_check("sweep_short_tma", K, c);
     }
     return fail(GSG_ERR_UNSUPPORTED, "internal: TMA short kernel not instantiated");
+}
+
+// PAIR tiles of pair j: y = alpha_a D_a x + alpha_b D_b x (+ y) on the sub-planes they cover
+template <int K>
+int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y, double alpha_a, double alpha_b,
+                double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        const SweepClass& c = pl.pairs[j];
+        auto kern = sweep_stream_kernel<K, true>;
+        static thread_local size_t configured = 0;
+        GSG_TRY(ensure_smem(kern, c.smem, configured));
+        const int grid = std::min(c.ntiles, pl.sm_count);
+        HDense<K> hd;
+        if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
+            return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
+        std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
+        GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p + 1, 0, sizeof(int), st));
+        kern<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha_a, alpha_b, beta != 0.0 ? 1 : 0, c.s2tiles.p, c.ntiles, hd,
+                                                    c.sprm, pl.tile_counter.p + 1, nullptr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return launch_check("sweep_stream(pair)", K, c);
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: pair kernel not instantiated");
 }
 
 template <int K, int P>
@@ -1055,8 +1211,8 @@ int elementwise_grid(const gsg_plan& pl, int64_t N) {
 
 // y = alpha * D_d x + beta * y   (d 0-based; device layout); x and y must not alias.  The launches
 // of one sweep write disjoint parts of y, so they are forked onto auxiliary streams and joined.
-int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y) {
-    const Direction& dir = pl.dirs[d];
+int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y, bool reduced = false) {
+    const Direction& dir = reduced ? pl.dirs_red[d] : pl.dirs[d];
     const size_t nc = dir.classes.size();
     if (beta != 0.0 && beta != 1.0) {     // kernels implement beta in {0, 1}
         scale_kernel<<<elementwise_grid(pl, pl.S.Npad), 256, 0, pl.stream>>>(pl.S.Npad, y, beta);
@@ -1104,8 +1260,58 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     return 0;
 }
 
+// y = sum_d c_d D_d x with the streaming classes of each direction pair fused (PAIR tiles) -- every c_d != 0
+int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y) {
+    const int K = pl.S.k, D = pl.S.D;
+    const int npairs = (int)pl.pairs.size();
+    for (int j = 0; j < npairs; ++j) {
+        const int da = 2 * j, db = da + 1;
+        const double beta = j == 0 ? 0.0 : 1.0;
+        // The PAIR tiles and the two reduced sweeps of this pair write disjoint cells (covered / not covered),
+        // so the PAIR kernel runs on its own stream beside them; pairs are joined one after the other because
+        // the next pair's tiles cover other cells.
+        // (Measured: running it beside them is slower, 4.47 vs 4.27 ms per step -- it competes with the reduced
+        // streaming kernels for the same L2 throughput and delays the long-pole CTAs; opt-in GSG_PAIR_OVERLAP.)
+        static const bool overlap = getenv("GSG_PAIR_OVERLAP") != nullptr;
+        cudaStream_t ps = overlap ? pl.aux.back() : pl.stream;
+        if (overlap) {
+            GSG_CUDA(cudaEventRecord(pl.ev_pair_fork, pl.stream));
+            GSG_CUDA(cudaStreamWaitEvent(ps, pl.ev_pair_fork, 0));
+            GSG_TRY(sweep(pl, da, c[da], x, beta, y, true));
+        }
+        switch (K) {
+            case 1: GSG_TRY(launch_pair<1>(pl, ps, j, x, y, c[da], c[db], beta)); break;
+            case 2: GSG_TRY(launch_pair<2>(pl, ps, j, x, y, c[da], c[db], beta)); break;
+            case 3: GSG_TRY(launch_pair<3>(pl, ps, j, x, y, c[da], c[db], beta)); break;
+            case 4: GSG_TRY(launch_pair<4>(pl, ps, j, x, y, c[da], c[db], beta)); break;
+            case 5: GSG_TRY(launch_pair<5>(pl, ps, j, x, y, c[da], c[db], beta)); break;
+            default: return fail(GSG_ERR_UNSUPPORTED, "internal: pair fusion for k > 5");
+        }
+        if (!overlap) GSG_TRY(sweep(pl, da, c[da], x, beta, y, true));
+        GSG_TRY(sweep(pl, db, c[db], x, 1.0, y, true));
+        if (overlap) {
+            GSG_CUDA(cudaEventRecord(pl.ev_pair_done, ps));
+            GSG_CUDA(cudaStreamWaitEvent(pl.stream, pl.ev_pair_done, 0));
+        }
+    }
+    for (int d = 2 * npairs; d < D; ++d) GSG_TRY(sweep(pl, d, c[d], x, d == 0 ? 0.0 : 1.0, y));
+    return 0;
+}
+
+bool can_fuse(const gsg_plan& pl, const double* c) {
+    if (pl.pairs.empty() || pl.pair_np < 0) return false;
+    for (int d = 0; d < pl.S.D; ++d)
+        if (c[d] == 0.0) return false;
+    return true;
+}
+
 // k = -sum_d a_d D_d w
 int advect_rhs(gsg_plan& pl, const double* a, const double* w, double* k) {
+    {
+        double c[16];
+        for (int d = 0; d < pl.S.D; ++d) c[d] = -a[d];
+        if (can_fuse(pl, c)) return grad_fused(pl, c, w, k);
+    }
     bool first = true;
     for (int d = 0; d < pl.S.D; ++d) {
         if (a[d] == 0.0 && !first) continue;
@@ -1366,6 +1572,8 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     GSG_CUDA(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
     P->stream = P->own_stream;
     GSG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    GSG_CUDA(cudaEventCreateWithFlags(&P->ev_pair_fork, cudaEventDisableTiming));
+    GSG_CUDA(cudaEventCreateWithFlags(&P->ev_pair_done, cudaEventDisableTiming));
     int prio_lo = 0, prio_hi = 0;     // long-pole CTAs first: they run beside the persistent streaming kernel
     GSG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     if (getenv("GSG_NO_PRIO")) prio_hi = prio_lo;
@@ -1378,7 +1586,8 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     GSG_TRY(P->tile_counter.resize(4));
     GSG_TRY(build_matrix(*P, H_n, H_colptr, H_rowval, H_nzval));
     P->dirs.resize(D);
-    for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d));
+    for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d, P->dirs[d], -1));
+    GSG_TRY(build_pairs(*P));
 
     // reconstruct tables
     std::vector<unsigned char> lv;
@@ -1406,6 +1615,8 @@ int gsg_plan_destroy(gsg_plan* plan) {
     for (cudaStream_t st : plan->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : plan->ev_done) if (ev) cudaEventDestroy(ev);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_pair_fork) cudaEventDestroy(plan->ev_pair_fork);
+    if (plan->ev_pair_done) cudaEventDestroy(plan->ev_pair_done);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     for (auto& pr : plan->prof_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (plan->step_exec) cudaGraphExecDestroy(plan->step_exec);
@@ -1467,7 +1678,8 @@ int gsg_plan_set_partition(gsg_plan* plan, int rank, int nranks) {
     plan->part_bits = bits;
     plan->dirs.clear();
     plan->dirs.resize(plan->S.D);
-    for (int d = 0; d < plan->S.D; ++d) GSG_TRY(build_direction(*plan, d));
+    for (int d = 0; d < plan->S.D; ++d) GSG_TRY(build_direction(*plan, d, plan->dirs[d], -1));
+    GSG_TRY(build_pairs(*plan));
     return 0;
 }
 
@@ -1638,6 +1850,7 @@ int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, do
 int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, double* y_dev) {
     GSG_TRY(check_plan(plan));
     if (!a || !x_dev || !y_dev || x_dev == y_dev) return fail(GSG_ERR_ARG, "bad pointers");
+    if (can_fuse(*plan, a)) return grad_fused(*plan, a, x_dev, y_dev);
     for (int d = 0; d < plan->S.D; ++d) GSG_TRY(sweep(*plan, d, a[d], x_dev, d == 0 ? 0.0 : 1.0, y_dev));
     return 0;
 }

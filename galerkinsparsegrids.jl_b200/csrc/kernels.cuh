@@ -516,12 +516,138 @@ __device__ __forceinline__ void short_tile_compute2(double* xs, const HDense<K>&
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Direction-pair fusion for the streaming classes.  For the pair (a, b = a+1) and fixed cells of the other
+// D-2 dimensions, the blocks with level_a + level_b <= n' (n' = n - sum of the other levels) form a 2-D
+// sparse sub-plane that is closed under the poles of BOTH directions; for n' <= 2 it has 1 / 3 / 8 multi-cells,
+// i.e. it fits one ring stage.  A PAIR tile holds whole sub-planes: y = alpha_a D_a x + alpha_b D_b x is formed
+// from ONE load of x and ONE store / reduce-add of y (the unfused sweeps move x twice and y three times).
+// One thread owns the k x k x (cells of the sub-plane) "mini-grid" of one combination of the other modes: all of
+// it sits in registers, so results are written back in place without any barrier.
+// Slot order of a sub-plane (shared with the host): for q_b = 0.., for q_a = 0.. with lvl(q_a) + lvl(q_b) <= n'.
+// ------------------------------------------------------------------------------------------
+namespace pairp {
+__host__ __device__ constexpr int lvl(int q) { return q == 0 ? 0 : (q == 1 ? 1 : (q < 4 ? 2 : 3)); }
+__host__ __device__ constexpr int ncell(int np) { return np == 0 ? 1 : (np == 1 ? 3 : 8); }
+// first slot of row q_b (branch-free in the optimiser's eyes: the unrolled loops must fold these to constants)
+__host__ __device__ constexpr int rowstart(int np, int qb) {
+    return np == 2 ? (qb == 0 ? 0 : (qb == 1 ? 4 : qb + 4)) : (np == 1 ? (qb == 0 ? 0 : 2) : 0);
+}
+__host__ __device__ constexpr int slot(int np, int qa, int qb) {      // -1 if (qa, qb) is not in the sub-plane
+    return (qa < (1 << np) && qb < (1 << np) && lvl(qa) + lvl(qb) <= np) ? rowstart(np, qb) + qa : -1;
+}
+}  // namespace pairp
+
+template <int K, int NPR, int QA, int QB>
+__device__ __forceinline__ void pair_cell_out(const HDense<K>& hd, const double (&x)[pairp::ncell(NPR)][K][K],
+                                              double* base, const int (&cofs)[pairp::ncell(NPR)], int Aa, int Ab,
+                                              double alpha_a, double alpha_b) {
+    constexpr int S = pairp::slot(NPR, QA, QB);
+    if constexpr (S >= 0) {
+        constexpr int PA = NPR - pairp::lvl(QB);          // pole class along a in row q_b
+        constexpr int PB = NPR - pairp::lvl(QA);          // pole class along b in column q_a
+        constexpr int NA = K << PA, NB = K << PB;
+        constexpr int HOA = ShortDims<K>::hoff(PA), HOB = ShortDims<K>::hoff(PB);
+#pragma unroll
+        for (int ma = 0; ma < K; ++ma)
+#pragma unroll
+            for (int mb = 0; mb < K; ++mb) {
+                double sa = 0.0, sb = 0.0;
+#pragma unroll
+                for (int qa2 = 0; qa2 < (1 << PA); ++qa2)
+#pragma unroll
+                    for (int m2 = 0; m2 < K; ++m2)
+                        sa = fma(hd.v[HOA + (QA * K + ma) * NA + qa2 * K + m2], x[pairp::slot(NPR, qa2, QB)][m2][mb], sa);
+#pragma unroll
+                for (int qb2 = 0; qb2 < (1 << PB); ++qb2)
+#pragma unroll
+                    for (int m2 = 0; m2 < K; ++m2)
+                        sb = fma(hd.v[HOB + (QB * K + mb) * NB + qb2 * K + m2], x[pairp::slot(NPR, QA, qb2)][ma][m2], sb);
+                base[cofs[S] + Aa * ma + Ab * mb] = fma(alpha_a, sa, alpha_b * sb);
+            }
+    }
+}
+
+template <int K, int NPR, int QB, int... QAs>
+__device__ __forceinline__ void pair_row_out(const HDense<K>& hd, const double (&x)[pairp::ncell(NPR)][K][K], double* base,
+                                             const int (&cofs)[pairp::ncell(NPR)], int Aa, int Ab, double alpha_a,
+                                             double alpha_b, std::integer_sequence<int, QAs...>) {
+    (pair_cell_out<K, NPR, QAs, QB>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b), ...);
+}
+
+template <int K, int NPR, int... QBs>
+__device__ __forceinline__ void pair_all_out(const HDense<K>& hd, const double (&x)[pairp::ncell(NPR)][K][K], double* base,
+                                             const int (&cofs)[pairp::ncell(NPR)], int Aa, int Ab, double alpha_a,
+                                             double alpha_b, std::integer_sequence<int, QBs...>) {
+    (pair_row_out<K, NPR, QBs>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b, std::make_integer_sequence<int, (1 << NPR)>{}), ...);
+}
+
+// one PAIR tile: nr sub-planes (items); cell (slot s, item r) sits at xs + (s*nr + r)*KDp
+template <int K, int NPR>
+__device__ __forceinline__ void pair_tile_compute(double* xs, const HDense<K>& hd, int nr, int KDp, int Aa, int NO,
+                                                  const int* pair_off, double alpha_a, double alpha_b, int ctid,
+                                                  int ncth) {
+    constexpr int NC = pairp::ncell(NPR);
+    const int Ab = K * Aa;
+    if constexpr (NPR == 2) {
+        // 8-cell sub-planes: one item per tile and only NO = k^(D-2) mini-grids, each 1188 DFMAs at k = 3 -- two
+        // warps share a mini-grid group (rows q_b = 0 / q_b >= 1 of the outputs) so that six of the eight warps work
+        const int wid = ctid >> 5, lane = ctid & 31, nw = ncth >> 5;     // nw is even: the halves (2m, 2m+1) of a
+        const int ngroups = (NO + 31) / 32;                               // group always run in the same round
+        const int total = nr * ngroups * 2;
+        for (int u0 = 0; u0 < total; u0 += nw) {
+            const int u = u0 + wid;
+            const int part = u & 1, og = (u >> 1) % ngroups, r = (u >> 1) / ngroups;
+            const int o = og * 32 + lane;
+            const bool valid = u < total && o < NO;
+            double* base = xs + (size_t)(valid ? r : 0) * KDp + pair_off[valid ? o : 0];
+            int cofs[NC];
+#pragma unroll
+            for (int sidx = 0; sidx < NC; ++sidx) cofs[sidx] = sidx * nr * KDp;
+            double x[NC][K][K];
+            if (valid) {
+#pragma unroll
+                for (int sidx = 0; sidx < NC; ++sidx)
+#pragma unroll
+                    for (int ma = 0; ma < K; ++ma)
+#pragma unroll
+                        for (int mb = 0; mb < K; ++mb) x[sidx][ma][mb] = base[cofs[sidx] + Aa * ma + Ab * mb];
+            }
+            // the two halves of a mini-grid are written by different warps: every compute thread passes this
+            // barrier (unconditionally) after reading its x and before any result of the round lands
+            asm volatile("bar.sync 1, %0;" ::"r"(ncth) : "memory");
+            if (valid) {
+                if (part == 0)
+                    pair_all_out<K, NPR>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b, std::integer_sequence<int, 0>{});
+                else
+                    pair_all_out<K, NPR>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b, std::integer_sequence<int, 1, 2, 3>{});
+            }
+        }
+        return;
+    }
+    for (int g = ctid; g < nr * NO; g += ncth) {
+        const int r = g / NO, o = g - r * NO;
+        double* base = xs + (size_t)r * KDp + pair_off[o];
+        int cofs[NC];
+#pragma unroll
+        for (int sidx = 0; sidx < NC; ++sidx) cofs[sidx] = sidx * nr * KDp;
+        double x[NC][K][K];
+#pragma unroll
+        for (int sidx = 0; sidx < NC; ++sidx)
+#pragma unroll
+            for (int ma = 0; ma < K; ++ma)
+#pragma unroll
+                for (int mb = 0; mb < K; ++mb) x[sidx][ma][mb] = base[cofs[sidx] + Aa * ma + Ab * mb];
+        pair_all_out<K, NPR>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b, std::make_integer_sequence<int, (1 << NPR)>{});
+    }
+}
+
 constexpr int STREAM_COMPUTE_WARPS = 8;
 constexpr int STREAM_THREADS = 32 * (STREAM_COMPUTE_WARPS + 2);
 
-template <int K>
+template <int K, bool PAIR>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
-sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double alpha_b, int accumulate,
                     const TileS2* __restrict__ tiles, int ntiles,
                     const __grid_constant__ HDense<K> hd, const ShortParams prm,
                     int* __restrict__ counter,       // dynamic tile scheduler (zeroed before the launch)
@@ -529,7 +655,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smraw);     // full[NS], done[NS], empty[NS]
     TileS2* sdesc = reinterpret_cast<TileS2*>(smraw + 128);                      // per-stage tile descriptor
-    const int PI = prm.KD / K;
+    const int PI = prm.KD / K;            // poles per item; PAIR: the table below holds PI / K mini-grid offsets
     int* pole_off = reinterpret_cast<int*>(smraw + 128 + 4 * sizeof(TileS2));
     size_t off = 128 + 4 * sizeof(TileS2) + (size_t)PI * 4;
     off = (off + 127) & ~(size_t)127;
@@ -542,9 +668,16 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     const int KDp = prm.KDp;
     const unsigned cell_bytes = (unsigned)KDp * 8u;
 
-    for (int j = tid; j < PI; j += blockDim.x) {
-        const int b = j / prm.A, a = j - b * prm.A;
-        pole_off[j] = a + K * prm.A * b;
+    if constexpr (PAIR) {                 // other-mode combination o -> in-cell offset (modes a, b = a+1 taken out)
+        for (int j = tid; j < PI / K; j += blockDim.x) {
+            const int b = j / prm.A, a = j - b * prm.A;
+            pole_off[j] = a + K * K * prm.A * b;
+        }
+    } else {
+        for (int j = tid; j < PI; j += blockDim.x) {
+            const int b = j / prm.A, a = j - b * prm.A;
+            pole_off[j] = a + K * prm.A * b;
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -653,6 +786,13 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
                 break;
             }
             double* xs = ring + (size_t)s * prm.stage_doubles;
+            if constexpr (PAIR) {
+                switch (P) {              // P = n' of the sub-planes in this tile
+                    case 0: pair_tile_compute<K, 0>(xs, hd, nr, KDp, prm.A, PI / K, pole_off, alpha, alpha_b, ctid, ncth); break;
+                    case 1: if constexpr (ShortDims<K>::pmax() >= 1) pair_tile_compute<K, 1>(xs, hd, nr, KDp, prm.A, PI / K, pole_off, alpha, alpha_b, ctid, ncth); break;
+                    case 2: if constexpr (ShortDims<K>::pmax() >= 2 && K <= 3) pair_tile_compute<K, 2>(xs, hd, nr, KDp, prm.A, PI / K, pole_off, alpha, alpha_b, ctid, ncth); break;
+                }
+            } else
             switch (P) {
                 case 0: short_tile_compute2<K, 0, 4>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
                 case 1: if constexpr (ShortDims<K>::pmax() >= 1) short_tile_compute2<K, 1, 2>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;

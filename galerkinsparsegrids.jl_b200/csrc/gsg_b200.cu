@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -970,9 +971,13 @@ int launch_check(const char* what, int K, const SweepClass& c) {
 template <class Kern>
 int ensure_smem(Kern kern, size_t smem, size_t& configured_unused) {
     (void)configured_unused;
-    static thread_local std::map<std::pair<const void*, int>, size_t> done;
+    // process-wide (the attribute is): a per-thread cache let a second host thread LOWER the limit a first
+    // thread had raised, and the first thread's next large launch failed with "invalid argument"
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
     int dev = 0;
     GSG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
     size_t& configured = done[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
     if (configured == 0) {
         // every sweep kernel asks for the maximum shared-memory carve-out: kernels with different

@@ -304,8 +304,11 @@ def test_full_size_baseline_config(gsg, oracle):
     rng = np.random.default_rng(7)
     x = rng.standard_normal(plan.size)
     y = rng.standard_normal(plan.size)
+    coef = np.array([1.0, -0.5, 0.25, 2.0, -1.5, 0.75])
+    grad_ref = np.zeros_like(x)
     for d in range(1, D + 1):
         Dx = plan.apply_D(d, x)
+        grad_ref += coef[d - 1] * Dx
         worst, lengths = 0.0, set()
         for idx in _sample_pole_indices(oracle, D, d, k, n, rng, 120):
             Np = idx.size
@@ -319,6 +322,8 @@ def test_full_size_baseline_config(gsg, oracle):
             assert relerr(plan.apply_D(d, 2.0 * x - 3.0 * y), 2.0 * Dx - 3.0 * Dy) <= 1e-13
             skew = abs(np.dot(x, Dy) + np.dot(Dx, y)) / (np.linalg.norm(x) * np.linalg.norm(Dy))
             assert skew < 1e-9
+    # the fused gradient (direction-pair tiles + reduced sweeps) against the sum of the single-direction applies
+    assert relerr(plan.apply_grad(coef, x), grad_ref) <= 1e-13
     # the two RK4 drivers (Taylor form / staged form) agree at full size, and the state moves
     a = np.ones(D)
     u0 = gsg.tensor_construct(D, k, n, [gsg.vcoeffs_DG(1, k, n, f_sin)] * D)
@@ -331,3 +336,19 @@ def test_full_size_baseline_config(gsg, oracle):
     # advection by a = (1,...,1) of prod sin(2 pi x_d) conserves the L2 norm to time-stepping accuracy
     assert abs(np.linalg.norm(u_taylor) / np.linalg.norm(u0) - 1.0) < 1e-6
     del plan
+
+
+@pytest.mark.parametrize("D,k,n", [(2, 3, 6), (4, 3, 5), (3, 2, 5), (2, 4, 4), (4, 1, 4), (2, 5, 3), (6, 3, 3)])
+def test_fused_gradient_matches_unfused(plans, oracle, D, k, n):
+    """gsg_apply_grad takes the direction-pair path when every coefficient is non-zero (PAIR tiles for the 2-D
+    sub-planes with n' <= 2 / 1 / 0 at k <= 3 / 4 / 5, reduced sweeps for the rest; odd D leaves the last
+    direction unpaired); a zero coefficient forces the plain per-direction path.  Both against the oracle."""
+    plan, H = plans(D, k, n, "sparse")
+    x = random_state(plan.size, seed=11 * D + k)
+    a = np.array([1.0, -0.5, 0.25, 2.0, -1.5, 0.75][:D])
+    ref = sum(a[d - 1] * oracle.apply_D_poles(D, d, k, n, x, H=H) for d in range(1, D + 1))
+    assert relerr(plan.apply_grad(a, x), ref) <= TOL
+    a0 = a.copy()
+    a0[0] = 0.0
+    ref0 = sum(a0[d - 1] * oracle.apply_D_poles(D, d, k, n, x, H=H) for d in range(1, D + 1))
+    assert relerr(plan.apply_grad(a0, x), ref0) <= TOL

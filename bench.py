@@ -301,9 +301,13 @@ def main():
             "bound": "hbm", "kernel": "sweep_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_prof,
-            "kernel_share_of_step": (prof_ms / n_prof) * (4 * D) / (ms / K),   # 4*D launches of it per step
-            "note": ("16 B/DOF algorithmic; 5 of 6 launches per RHS accumulate (y += via TMA reduce-add), whose real "
-                     "HBM traffic is 24 B/DOF; timed: the first launches of the timed region (bounded sample)"),
+            # per step: 4 RHS x (D/2 PAIR launches + D reduced launches) of this kernel family
+            "kernel_share_of_step": (prof_ms / n_prof) * (4 * (D + D // 2)) / (ms / K),
+            "note": ("sweep_stream_kernel<K, PAIR> family: per RHS D/2 direction-pair launches (2-D sub-planes with "
+                     "n' <= 2, two directional applies from one load / one store) + D launches over the remaining "
+                     "short-pole groups; algorithmic = 16 B per DOF per directional apply (SURVEY 8d), so a PAIR "
+                     "launch counts 32 B/DOF while moving 16-24; 'traffic' = ncu DRAM bytes per launch averaged over "
+                     "one RHS; timed: the first launches of the timed region (bounded sample)"),
             "step_model": {"bytes_per_dof_model": 64 * D + 144,
                            "achieved_gbs": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9,
                            "frac": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9 / peak},

@@ -1049,7 +1049,7 @@ int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y
         GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p + 1, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
-        kern<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha_a, alpha_b, beta != 0.0 ? 1 : 0, c.s2tiles.p, c.ntiles, hd,
+        kern<<<grid, StreamCfg<true>::THREADS, c.smem, st>>>(x, y, alpha_a, alpha_b, beta != 0.0 ? 1 : 0, c.s2tiles.p, c.ntiles, hd,
                                                     c.sprm, pl.tile_counter.p + 1, nullptr);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, st));

@@ -642,11 +642,19 @@ __device__ __forceinline__ void pair_tile_compute(double* xs, const HDense<K>& h
     }
 }
 
+// compute warps: 8 for the single-direction tiles; 6 for PAIR tiles (256 threads leave 255 registers per thread:
+// the 72-value mini-grid of an 8-cell sub-plane then stays in registers; with 320 threads the cap is 168 and
+// ptxas spilled 560 bytes)
+template <bool PAIR>
+struct StreamCfg {
+    static constexpr int CW = PAIR ? 6 : 8;
+    static constexpr int THREADS = 32 * (CW + 2);
+};
 constexpr int STREAM_COMPUTE_WARPS = 8;
 constexpr int STREAM_THREADS = 32 * (STREAM_COMPUTE_WARPS + 2);
 
 template <int K, bool PAIR>
-__global__ void __launch_bounds__(STREAM_THREADS, 1)
+__global__ void __launch_bounds__(StreamCfg<PAIR>::THREADS, 1)
 sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double alpha_b, int accumulate,
                     const TileS2* __restrict__ tiles, int ntiles,
                     const __grid_constant__ HDense<K> hd, const ShortParams prm,
@@ -682,7 +690,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             tma::mbar_init(tma::smem_u32(&bars[s]), 1);
-            tma::mbar_init(tma::smem_u32(&bars[4 + s]), STREAM_COMPUTE_WARPS);
+            tma::mbar_init(tma::smem_u32(&bars[4 + s]), StreamCfg<PAIR>::CW);
             tma::mbar_init(tma::smem_u32(&bars[8 + s]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -773,7 +781,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
         }
     } else {
         // ================= compute warps =================
-        const int ctid = tid - 64, ncth = 32 * STREAM_COMPUTE_WARPS;
+        const int ctid = tid - 64, ncth = 32 * StreamCfg<PAIR>::CW;
         for (int it = 0;; ++it) {
             const int s = it % NS;
             const long long w0 = clock64();

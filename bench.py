@@ -258,8 +258,8 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     # CUDA events around the dominant kernel for a bounded sample of the timed region's launches (the first
-    # ~6 steps' worth: timing all of them costs ~8 % of the step)
-    plan.profile_enable(0 if os.environ.get("GSG_NO_PROFILE_EVENTS") else 144)
+    # 72 = two steps' worth: timing all of them costs ~8 % of the step, this sample ~0.5 %)
+    plan.profile_enable(0 if os.environ.get("GSG_NO_PROFILE_EVENTS") else 72)
     l0 = g.launch_count()
     sampler.start()
     barrier()

@@ -98,6 +98,7 @@ struct SweepClass {          // one launch of a sweep
     int rsplit = 1;          // long kernel: row parts (CTAs) per pole set
     int cpl = 1;             // register-tiled long kernel: poles per lane
     int npass = 1;           // ... and column passes
+    int nbuf = 4;            // ... and record-ring depth (2 with 16 warps)
     std::vector<std::unique_ptr<DevBuf<int>>> passBlk, passRow;
     DevBuf<TileL2> l2tiles;
     DevBuf<int> partBlk, partRow;
@@ -625,11 +626,16 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
             const size_t xtile = (size_t)(NP / npass) * 32 * C * 8;
             // ~190 registers per thread at C = 4: small CTAs (several per SM) while the tile is small
             int nw2 = (C >= 4 && xtile <= 50 * 1024) ? 4 : 8;
-            if (const char* e = getenv("GSG_LONG_NW")) nw2 = atoi(e);
-            nw2 = std::max(1, std::min(nw2, 8));
-            const size_t ring_bytes = (size_t)LONG_NBUF * LONG_CH * REC;
+            // C <= 2 (<= 128 registers): a CTA with a big x tile owns its SM, and 8 warps leave the record loop
+            // latency-bound (~2.7x its shared-memory bound at N' = 384) -- run 16 warps with a 2-deep ring
+            int nbuf = LONG_NBUF;
+            if (K <= 3 && C <= 2 && xtile > 100 * 1024 && NQ >= 64 && !getenv("GSG_LONG_NO16")) { nw2 = 16; nbuf = 2; }
+            if (const char* e = getenv("GSG_LONG_NW")) nw2 = std::min(atoi(e), nbuf == 2 ? 16 : 8);
+            nw2 = std::max(1, std::min(nw2, nbuf == 2 ? 16 : 8));
+            const size_t ring_bytes = (size_t)nbuf * LONG_CH * REC;
             while (nw2 > 2 && xtile + nw2 * ring_bytes + 2048 > SMEM_OPTIN_MAX) nw2 >>= 1;
             const size_t smem2 = xtile + nw2 * ring_bytes;
+            c.nbuf = nbuf;
             if (smem2 + 2048 <= SMEM_OPTIN_MAX && (C == 1 || C == 2 || C == 4)) {
                 c.kind = Kind::LONG2;
                 c.cpl = C;
@@ -1109,10 +1115,10 @@ int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swe
     return fail(GSG_ERR_UNSUPPORTED, "internal: long kernel not instantiated");
 }
 
-template <int K, int C>
+template <int K, int C, int NB>
 int launch_long2_kc(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                     double* y, double alpha, double beta) {
-    auto kern = sweep_long2_kernel<K, C>;
+    auto kern = sweep_long2_kernel<K, C, NB>;
     static thread_local size_t configured = 0;
     GSG_TRY(ensure_smem(kern, c.smem, configured));
     int tb, tn;
@@ -1136,10 +1142,19 @@ template <int K>
 int launch_long2_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                    double* y, double alpha, double beta) {
     if constexpr (K >= 1 && K <= 5) {
+        if (c.nbuf == 2) {
+            if constexpr (K <= 3) {
+                switch (c.cpl) {
+                    case 1: return launch_long2_kc<K, 1, 2>(pl, st, dir, c, x, y, alpha, beta);
+                    case 2: return launch_long2_kc<K, 2, 2>(pl, st, dir, c, x, y, alpha, beta);
+                }
+            }
+            return fail(GSG_ERR_UNSUPPORTED, "internal: 16-warp long kernel not instantiated");
+        }
         switch (c.cpl) {
-            case 1: return launch_long2_kc<K, 1>(pl, st, dir, c, x, y, alpha, beta);
-            case 2: return launch_long2_kc<K, 2>(pl, st, dir, c, x, y, alpha, beta);
-            case 4: if constexpr (K <= 3) return launch_long2_kc<K, 4>(pl, st, dir, c, x, y, alpha, beta); break;
+            case 1: return launch_long2_kc<K, 1, 4>(pl, st, dir, c, x, y, alpha, beta);
+            case 2: return launch_long2_kc<K, 2, 4>(pl, st, dir, c, x, y, alpha, beta);
+            case 4: if constexpr (K <= 3) return launch_long2_kc<K, 4, 4>(pl, st, dir, c, x, y, alpha, beta); break;
         }
     }
     return fail(GSG_ERR_UNSUPPORTED, "internal: register-tiled long kernel not instantiated");

@@ -1142,8 +1142,9 @@ __device__ __forceinline__ int2 lds_v2s32(unsigned addr) {
     return r;
 }
 
-template <int K, int C>
-__global__ void __launch_bounds__(256)
+// NB = depth of the per-warp record ring: 4 (8 warps) or 2 (16 warps next to a 196 KB x tile)
+template <int K, int C, int NB>
+__global__ void __launch_bounds__(NB == 2 ? 512 : 256)
 sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                    const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
                    const TileL2* __restrict__ tiles, const unsigned char* __restrict__ recs,
@@ -1153,7 +1154,7 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
                    long long* __restrict__ dbg) {     // dbg: optional per-warp clock stamps (first 8 CTAs)
     constexpr int KK = K * K, REC = LongRec<K>::BYTES;
     constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
-    constexpr int RINGREC = LONG_CH * LONG_NBUF;              // records the ring holds
+    constexpr int RINGREC = LONG_CH * NB;              // records the ring holds
     constexpr int PT = 32 * C;
     const long long t_start = clock64();
     const long long g_t0 = dbg ? gtimer() : 0;
@@ -1166,7 +1167,7 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     int lane = tid & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));
     double* xs = reinterpret_cast<double*>(smraw);                                  // NP * PT
-    unsigned char* ring = smraw + (size_t)NP * PT * 8 + (size_t)warp * (LONG_NBUF * CHB);
+    unsigned char* ring = smraw + (size_t)NP * PT * 8 + (size_t)warp * (NB * CHB);
     unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     unsigned xs_s = (unsigned)__cvta_generic_to_shared(xs) + lane * 8;
     // opaque copies: stops the compiler from rematerialising these bases (S2R + IMADs) per record
@@ -1183,14 +1184,13 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     auto issue_chunk = [&](int c) {
         if (c <= c_last) {
             const unsigned char* src = recs + (size_t)c * CHB;
-            const unsigned dst = ring_s + (c % LONG_NBUF) * CHB;
+            const unsigned dst = ring_s + (c % NB) * CHB;
             for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
         }
         cp_async_commit();
     };
-    issue_chunk(c_first);
-    issue_chunk(c_first + 1);
-    issue_chunk(c_first + 2);
+#pragma unroll
+    for (int j = 0; j < NB - 1; ++j) issue_chunk(c_first + j);
 
     // per-lane pole constants (no integer divisions: the tile carries its first item / pole)
     long long u[C], v[C];
@@ -1250,10 +1250,10 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
     auto fetch = [&](int i, LongOperands<K, C>& o) {
         if ((i & (LONG_CH - 1)) == 0 || i == b0) {
             // entering chunk ci: every lane has finished reading chunk ci-1 (its last record is in
-            // registers), so that buffer is refilled with chunk ci+3; then chunk ci must have landed
+            // registers), so that buffer is refilled with chunk ci+NB-1; then chunk ci must have landed
             __syncwarp();
-            issue_chunk(i / LONG_CH + 3);
-            cp_async_wait<3>();
+            issue_chunk(i / LONG_CH + NB - 1);
+            cp_async_wait<NB - 1>();
             __syncwarp();
         }
         const unsigned ra = ring_s + (i & (RINGREC - 1)) * REC;

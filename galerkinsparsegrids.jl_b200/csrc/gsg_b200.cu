@@ -623,6 +623,14 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
                 npass = 1;
                 while (C > 1 && (size_t)NP * 32 * C * 8 > xcap) C >>= 1;
             }
+            // experiment: where C = 4 needs a tile above 100 KB (one 8-warp CTA per SM), take C = 2 with a 2-deep
+            // ring instead so that two CTAs (16 warps) share the SM
+            bool two_per_sm = false;
+            if (getenv("GSG_LONG_HALF") && K <= 3 && C == 4 && (size_t)(NP / npass) * 32 * C * 8 > 100 * 1024 &&
+                (size_t)(NP / npass) * 32 * 2 * 8 <= 100 * 1024) {
+                C = 2;
+                two_per_sm = true;
+            }
             const size_t xtile = (size_t)(NP / npass) * 32 * C * 8;
             // ~190 registers per thread at C = 4: small CTAs (several per SM) while the tile is small
             int nw2 = (C >= 4 && xtile <= 50 * 1024) ? 4 : 8;
@@ -630,6 +638,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
             // latency-bound (~2.7x its shared-memory bound at N' = 384) -- run 16 warps with a 2-deep ring
             int nbuf = LONG_NBUF;
             if (K <= 3 && C <= 2 && xtile > 100 * 1024 && NQ >= 64 && !getenv("GSG_LONG_NO16")) { nw2 = 16; nbuf = 2; }
+            if (two_per_sm) { nw2 = 8; nbuf = 2; }
             if (const char* e = getenv("GSG_LONG_NW")) nw2 = std::min(atoi(e), nbuf == 2 ? 16 : 8);
             nw2 = std::max(1, std::min(nw2, nbuf == 2 ? 16 : 8));
             const size_t ring_bytes = (size_t)nbuf * LONG_CH * REC;

@@ -406,6 +406,14 @@ class Plan:
         a = _f64(a)
         check(lib.gsg_apply_grad_dev(self._h, _ptr(a), _devptr(x), _devptr(y)))
 
+    def apply_dirs_dev(self, c, dirs, x, y, beta: float = 0.0) -> None:
+        """y = beta*y + sum_{d in dirs} c[d-1] D_d x (1-based directions; pairs inside `dirs` are swept fused)."""
+        c = _f64(c)
+        mask = 0
+        for d in dirs:
+            mask |= 1 << (d - 1)
+        check(lib.gsg_apply_dirs_dev(self._h, _ptr(c), mask, float(beta), _devptr(x), _devptr(y)))
+
     def apply_laplacian_dev(self, x, y, tmp) -> None:
         check(lib.gsg_apply_laplacian_dev(self._h, _devptr(x), _devptr(y), _devptr(tmp)))
 

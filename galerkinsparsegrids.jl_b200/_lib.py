@@ -62,6 +62,7 @@ SIGNATURES = {
     "gsg_apply_D_dev": (i32, [vp, i32, f64, vp, f64, vp]),
     "gsg_apply_grad_dev": (i32, [vp, vp, vp, vp]),
     "gsg_apply_laplacian_dev": (i32, [vp, vp, vp, vp]),
+    "gsg_apply_dirs_dev": (i32, [vp, vp, C.c_uint, f64, vp, vp]),
     "gsg_rk4_advect": (i32, [vp, vp, vp, f64, i64]),
     "gsg_rk4_advect_dev": (i32, [vp, vp, vp, f64, i64]),
     "gsg_rk4_wave": (i32, [vp, vp, vp, f64, i64]),

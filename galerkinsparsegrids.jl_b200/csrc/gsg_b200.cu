@@ -846,7 +846,7 @@ int build_pairs(gsg_plan& P) {
     P.pair_np = -1;
     P.pairs.clear();
     P.dirs_red.clear();
-    if (getenv("GSG_NO_PAIR") || S.scheme != 0 || D < 2 || K > 5 || P.short_pmax < 0 || P.part_bits > 0) return 0;
+    if (getenv("GSG_NO_PAIR") || S.scheme != 0 || D < 2 || K > 5 || P.short_pmax < 0) return 0;
     int npmax = K <= 3 ? 2 : (K == 4 ? 1 : 0);
     npmax = std::min(npmax, std::min(P.short_pmax, n));
     if (const char* e = getenv("GSG_PAIR_NP")) npmax = std::min(npmax, atoi(e));
@@ -862,6 +862,14 @@ int build_pairs(gsg_plan& P) {
         c.kind = Kind::SHORT_TMA;
         c.stream2 = true;
         std::vector<TileS2> tl;
+        // block partition: a pair that contains a partition dimension is not fused (its poles straddle ranks);
+        // otherwise a sub-plane belongs to the rank that owns its blocks (ownership depends on the other levels)
+        bool pair_has_partition_dim = false;
+        for (int jb = 0; jb < P.part_bits; ++jb) {
+            const int e = D - 1 - jb;
+            if (e == da || e == db) pair_has_partition_dim = true;
+        }
+        if (pair_has_partition_dim) { c.ntiles = 0; continue; }
         for (int np = npmax; np >= 0; --np) {                     // largest sub-planes first
             const int NC = pairp::ncell(np), nr_max = CT / NC;
             // plane groups: levels of the other dims with n - sum == np; representative = the (0, 0) block
@@ -870,6 +878,12 @@ int build_pairs(gsg_plan& P) {
                 int s_other = 0;
                 for (int i = 0; i < D; ++i) s_other += b0.level[i];
                 if (n - s_other != np) continue;
+                bool mine = true;
+                for (int jb = 0; jb < P.part_bits; ++jb) {
+                    const int e = D - 1 - jb;
+                    mine = mine && ((b0.level[e] == 0) == (((P.part_rank >> jb) & 1) == 1));
+                }
+                if (!mine) continue;
                 long long nitems = 1;
                 for (int i = 0; i < D; ++i)
                     if (i != da && i != db) nitems *= b0.cells[i];
@@ -940,7 +954,10 @@ int build_pairs(gsg_plan& P) {
             }
         }
         c.ntiles = (int)tl.size();
-        if (c.ntiles == 0) { P.pairs.clear(); return 0; }
+        if (c.ntiles == 0) {
+            if (P.part_bits == 0) { P.pairs.clear(); return 0; }
+            continue;                       // this rank owns no sub-plane of the pair
+        }
         GSG_TRY(c.s2tiles.upload(tl));
         const int PI = KD / K;
         const size_t fixed = 128 + std::max(8 * sizeof(TileS), 4 * sizeof(TileS2)) + (size_t)PI * 4 + 128;
@@ -956,7 +973,14 @@ int build_pairs(gsg_plan& P) {
     }
     P.pair_np = npmax;
     P.dirs_red.resize(2 * npairs);
-    for (int d = 0; d < 2 * npairs; ++d) GSG_TRY(build_direction(P, d, P.dirs_red[d], npmax));
+    for (int d = 0; d < 2 * npairs; ++d) {
+        bool fused = true;                  // pairs holding a partition dimension keep their complete tables
+        for (int jb = 0; jb < P.part_bits; ++jb) {
+            const int e = D - 1 - jb;
+            if (e == (d & ~1) || e == (d | 1)) fused = false;
+        }
+        GSG_TRY(build_direction(P, d, P.dirs_red[d], fused ? npmax : -1));
+    }
     return 0;
 }
 
@@ -1297,25 +1321,35 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
 }
 
 // y = sum_d c_d D_d x with the streaming classes of each direction pair fused (PAIR tiles) -- every c_d != 0
-int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y) {
+// y = beta0 * y + sum_{d in mask} c_d D_d x with the streaming classes of each direction pair fused (PAIR tiles)
+// where both directions of the pair are in the mask; every c_d in the mask must be non-zero
+int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y, unsigned mask = ~0u, double beta0 = 0.0) {
     const int K = pl.S.k, D = pl.S.D;
     const int npairs = (int)pl.pairs.size();
+    bool first = true;
+    auto next_beta = [&]() { const double b = first ? beta0 : 1.0; first = false; return b; };
     for (int j = 0; j < npairs; ++j) {
         const int da = 2 * j, db = da + 1;
-        const double beta = j == 0 ? 0.0 : 1.0;
-        // The PAIR tiles and the two reduced sweeps of this pair write disjoint cells (covered / not covered),
-        // so the PAIR kernel runs on its own stream beside them; pairs are joined one after the other because
-        // the next pair's tiles cover other cells.
-        // (Measured: running it beside them is slower, 4.47 vs 4.27 ms per step -- it competes with the reduced
-        // streaming kernels for the same L2 throughput and delays the long-pole CTAs; opt-in GSG_PAIR_OVERLAP.)
+        const bool ina = (mask >> da) & 1, inb = (mask >> db) & 1;
+        if (!(ina && inb)) {              // at most one direction of the pair: plain sweeps (complete tables)
+            if (ina) GSG_TRY(sweep(pl, da, c[da], x, next_beta(), y));
+            if (inb) GSG_TRY(sweep(pl, db, c[db], x, next_beta(), y));
+            continue;
+        }
+        const double beta = next_beta();
+        // The PAIR tiles and the two reduced sweeps of this pair write disjoint cells (covered / not covered);
+        // pairs are processed one after the other because the next pair's tiles cover other cells.
+        // (Measured: running the PAIR kernel on its own stream beside the sweeps is slower, 4.47 vs 4.27 ms per
+        // step -- it competes for the same L2 throughput and delays the long-pole CTAs; opt-in GSG_PAIR_OVERLAP.)
         static const bool overlap = getenv("GSG_PAIR_OVERLAP") != nullptr;
+        const bool has_tiles = pl.pairs[j].ntiles > 0;
         cudaStream_t ps = overlap ? pl.aux.back() : pl.stream;
         if (overlap) {
             GSG_CUDA(cudaEventRecord(pl.ev_pair_fork, pl.stream));
             GSG_CUDA(cudaStreamWaitEvent(ps, pl.ev_pair_fork, 0));
             GSG_TRY(sweep(pl, da, c[da], x, beta, y, true));
         }
-        switch (K) {
+        if (has_tiles) switch (K) {
             case 1: GSG_TRY(launch_pair<1>(pl, ps, j, x, y, c[da], c[db], beta)); break;
             case 2: GSG_TRY(launch_pair<2>(pl, ps, j, x, y, c[da], c[db], beta)); break;
             case 3: GSG_TRY(launch_pair<3>(pl, ps, j, x, y, c[da], c[db], beta)); break;
@@ -1330,14 +1364,15 @@ int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y) {
             GSG_CUDA(cudaStreamWaitEvent(pl.stream, pl.ev_pair_done, 0));
         }
     }
-    for (int d = 2 * npairs; d < D; ++d) GSG_TRY(sweep(pl, d, c[d], x, d == 0 ? 0.0 : 1.0, y));
+    for (int d = 2 * npairs; d < D; ++d)
+        if ((mask >> d) & 1) GSG_TRY(sweep(pl, d, c[d], x, next_beta(), y));
     return 0;
 }
 
-bool can_fuse(const gsg_plan& pl, const double* c) {
+bool can_fuse(const gsg_plan& pl, const double* c, unsigned mask = ~0u) {
     if (pl.pairs.empty() || pl.pair_np < 0) return false;
     for (int d = 0; d < pl.S.D; ++d)
-        if (c[d] == 0.0) return false;
+        if (((mask >> d) & 1) && c[d] == 0.0) return false;
     return true;
 }
 
@@ -1888,6 +1923,26 @@ int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, dou
     if (!a || !x_dev || !y_dev || x_dev == y_dev) return fail(GSG_ERR_ARG, "bad pointers");
     if (can_fuse(*plan, a)) return grad_fused(*plan, a, x_dev, y_dev);
     for (int d = 0; d < plan->S.D; ++d) GSG_TRY(sweep(*plan, d, a[d], x_dev, d == 0 ? 0.0 : 1.0, y_dev));
+    return 0;
+}
+
+// y = beta * y + sum over the directions d (1-based) whose bit (d-1) is set in dmask of c[d-1] * D_d x; beta in
+// {0, 1}.  Direction pairs that lie inside the mask are swept fused (one load of x, one store of y).
+int gsg_apply_dirs_dev(gsg_plan* plan, const double* c, unsigned dmask, double beta, const double* x_dev,
+                       double* y_dev) {
+    GSG_TRY(check_plan(plan));
+    if (!c || !x_dev || !y_dev || x_dev == y_dev) return fail(GSG_ERR_ARG, "bad pointers");
+    if (beta != 0.0 && beta != 1.0) return fail(GSG_ERR_ARG, "beta must be 0 or 1");
+    const int D = plan->S.D;
+    dmask &= (D >= 32 ? ~0u : ((1u << D) - 1u));
+    if (dmask == 0) return 0;
+    if (can_fuse(*plan, c, dmask)) return grad_fused(*plan, c, x_dev, y_dev, dmask, beta);
+    bool first = true;
+    for (int d = 0; d < D; ++d) {
+        if (!((dmask >> d) & 1)) continue;
+        GSG_TRY(sweep(*plan, d, c[d], x_dev, first ? beta : 1.0, y_dev));
+        first = false;
+    }
     return 0;
 }
 

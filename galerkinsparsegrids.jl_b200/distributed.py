@@ -293,14 +293,11 @@ class PartitionedRK4:
         local = [d for d in range(1, self.D + 1) if d not in self.ex]
         any_local = any(self.a[d - 1] != 0.0 for d in local) or not self.ex
 
+        neg_a = [-x for x in self.a]
+
         def local_sweeps():
-            first = True
-            for d in local:
-                ad = self.a[d - 1]
-                if ad == 0.0 and not first:
-                    continue
-                plan.apply_D_dev(d, w, k, alpha=-ad, beta=0.0 if first else 1.0)
-                first = False
+            dirs = [d for d in local if self.a[d - 1] != 0.0] or local[:1]
+            plan.apply_dirs_dev(neg_a, dirs, w, k, 0.0)       # direction pairs inside `dirs` are swept fused
 
         def partition_sweeps():
             first = not any_local

@@ -109,6 +109,10 @@ int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, do
 /* y = sum_d a[d] D_d x */
 int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, double* y_dev);
 int gsg_apply_laplacian_dev(gsg_plan* plan, const double* x_dev, double* y_dev, double* tmp_dev);
+/* y = beta * y + sum of c[d-1] * D_d x over the directions d whose bit (d-1) is set in dmask (beta 0 or 1);
+ * direction pairs inside the mask are swept fused.  Used by the multi-GPU driver (local / partition groups). */
+int gsg_apply_dirs_dev(gsg_plan* plan, const double* c, unsigned dmask, double beta, const double* x_dev,
+                       double* y_dev);
 
 /* RK4 driver variant: 0 (default) = automatic -- the linear right-hand sides below are advanced in the
  * Taylor form u += dt L u + dt^2/2 L^2 u + dt^3/6 L^3 u + dt^4/24 L^4 u (same four operator applies,

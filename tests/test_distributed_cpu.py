@@ -171,6 +171,12 @@ class OraclePartPlan:
         kn = k.numpy()
         kn[idx] = alpha * y[idx] + (beta * kn[idx] if beta != 0.0 else 0.0)
 
+    def apply_dirs_dev(self, c, dirs, w, k, beta=0.0):
+        first = True
+        for d in dirs:
+            self.apply_D_dev(d, w, k, alpha=c[d - 1], beta=beta if first else 1.0)
+            first = False
+
     def rk4_taylor_cells_dev(self, cells, u, v1, v2, v3, v4, c1, c2, c3, c4):
         cs = self.cell_stride
         idx = (cells.numpy().astype(np.int64)[:, None] * cs + np.arange(cs)[None, :]).reshape(-1)

@@ -582,6 +582,14 @@ __device__ __forceinline__ void pair_all_out(const HDense<K>& hd, const double (
     (pair_row_out<K, NPR, QBs>(hd, x, base, cofs, Aa, Ab, alpha_a, alpha_b, std::make_integer_sequence<int, (1 << NPR)>{}), ...);
 }
 
+// n' = 2 sub-planes: split a mini-grid's output rows over two warps (needs a named barrier among the compute
+// warps between the reads and the in-place writes).  Compile with -DGSG_PAIR_SPLIT_ROWS=0 for the barrier-free
+// variant (one thread per mini-grid, all 72 outputs): ptxas then spills 728 bytes even at 255 registers.
+#ifndef GSG_PAIR_SPLIT_ROWS
+#define GSG_PAIR_SPLIT_ROWS 1
+#endif
+constexpr bool PAIR_SPLIT_ROWS = GSG_PAIR_SPLIT_ROWS != 0;
+
 // one PAIR tile: nr sub-planes (items); cell (slot s, item r) sits at xs + (s*nr + r)*KDp
 template <int K, int NPR>
 __device__ __forceinline__ void pair_tile_compute(double* xs, const HDense<K>& hd, int nr, int KDp, int Aa, int NO,
@@ -589,7 +597,7 @@ __device__ __forceinline__ void pair_tile_compute(double* xs, const HDense<K>& h
                                                   int ncth) {
     constexpr int NC = pairp::ncell(NPR);
     const int Ab = K * Aa;
-    if constexpr (NPR == 2) {
+    if constexpr (NPR == 2 && PAIR_SPLIT_ROWS) {
         // 8-cell sub-planes: one item per tile and only NO = k^(D-2) mini-grids, each 1188 DFMAs at k = 3 -- two
         // warps share a mini-grid group (rows q_b = 0 / q_b >= 1 of the outputs) so that six of the eight warps work
         const int wid = ctid >> 5, lane = ctid & 31, nw = ncth >> 5;     // nw is even: the halves (2m, 2m+1) of a

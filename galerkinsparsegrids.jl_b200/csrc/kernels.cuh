@@ -13,6 +13,15 @@
 // DEVICE LAYOUT: identical to the reference's vector layout (src/dg_vmethods.jl:48-73) except
 // that every multi-cell is padded from KD to KDp = KD rounded up to even, so that every cell
 // starts on a 16-byte boundary (TMA bulk copies, 128-bit accesses).
+//
+// Kernels in this file, by pole length N' = K * 2^p of the class they serve:
+//   sweep_stream_kernel<K, PAIR>   N' <= 32   persistent TMA ring (loader / storer / compute warps); PAIR = one
+//                                             pass for both directions of a pair over 2-D sub-planes (n' <= 2)
+//   sweep_consth_kernel<K, P>      N' = 48    matrix unrolled into constant-bank operands (structural pattern)
+//   sweep_long2_kernel<K, C, NB>   N' >= 96   register-tiled: lanes = poles, C poles per lane, record stream
+//   sweep_short_tma_kernel, sweep_short_kernel, sweep_long_kernel, sweep_generic_kernel   first generation / fallbacks
+//   rk_stage_kernel, rk_final_kernel, rk4_taylor_kernel(_cells)   RK4 updates
+//   reconstruct2_kernel (reconstruct_kernel)   batched reconstruct_DG;   spmv_csr_kernel   cross-check SpMV
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -176,9 +176,10 @@ def run_reference(args, D, k, n, rank, world):
         return
     ncores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    results = [cpu_baseline(D, k, n, 1, budget_s=12.0)]
+    budget = float(os.environ.get("GSG_CPU_BUDGET_S", "12"))        # seconds of CPU work per variant
+    results = [cpu_baseline(D, k, n, 1, budget_s=budget)]
     if ncores > 1:
-        results.append(cpu_baseline(D, k, n, ncores, budget_s=12.0))
+        results.append(cpu_baseline(D, k, n, ncores, budget_s=budget))
     best = max(results, key=lambda r: r["value"])
     N = results[0]["t_step_est_s"] * results[0]["value"]
     line = {

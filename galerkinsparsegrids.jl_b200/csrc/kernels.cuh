@@ -706,7 +706,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     }
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            tma::mbar_init(tma::smem_u32(&bars[s]), 1);
+            tma::mbar_init(tma::smem_u32(&bars[s]), 32);      // every loader lane writes descriptor words and arrives
             tma::mbar_init(tma::smem_u32(&bars[4 + s]), StreamCfg<PAIR>::CW);
             tma::mbar_init(tma::smem_u32(&bars[8 + s]), 1);
         }
@@ -740,17 +740,17 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
             int* dw = reinterpret_cast<int*>(&sdesc[s]);
             const unsigned bar = tma::smem_u32(&bars[s]);
             if (idx >= ntiles) {
-                if (lane == 0) {
-                    sdesc[s].P = -1;
-                    tma::mbar_arrive(bar);          // release the compute warps without data
-                }
+                if (lane == 0) sdesc[s].P = -1;
+                tma::mbar_arrive(bar);              // release the compute warps without data (all 32 lanes arrive)
                 break;
             }
             dw[lane] = w0;
             if (lane + 32 < TILE2_WORDS) dw[lane + 32] = w1;
             __syncwarp();
             const TileS2& t = sdesc[s];
+            // each lane's arrive releases the descriptor words it wrote; lane 0's also posts the byte count
             if (lane == 0) tma::mbar_expect_tx(bar, (unsigned)t.ncell * cell_bytes);
+            else tma::mbar_arrive(bar);
             __syncwarp();
             if (lane < t.nruns) {
                 const TileS2::Run rn = t.run[lane];

@@ -356,9 +356,6 @@ class Plan:
                                            _devptr(v2), _devptr(v3), _devptr(v4), float(c1), float(c2), float(c3),
                                            float(c4)))
 
-    def set_shard(self, rank: int, nranks: int) -> None:
-        check(lib.gsg_plan_set_shard(self._h, rank, nranks))
-
     def rk_stage_dev(self, length: int, u, k, acc, w, cw: float, ca: float, first: bool) -> None:
         check(lib.gsg_rk_stage_dev(self._h, int(length), _devptr(u), _devptr(k), _devptr(acc), _devptr(w),
                                    float(cw), float(ca), 1 if first else 0))

@@ -68,7 +68,6 @@ SIGNATURES = {
     "gsg_rk4_wave": (i32, [vp, vp, vp, f64, i64]),
     "gsg_rk4_wave_dev": (i32, [vp, vp, vp, f64, i64]),
     "gsg_energy": (i32, [vp, vp, vp, p_f64]),
-    "gsg_plan_set_shard": (i32, [vp, i32, i32]),
     "gsg_plan_set_partition": (i32, [vp, i32, i32]),
     "gsg_plan_partition_blocks": (i32, [vp, i32, i32, vp, vp, p_i64, C.POINTER(i32)]),
     "gsg_rk4_taylor_cells_dev": (i32, [vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64]),
@@ -77,6 +76,8 @@ SIGNATURES = {
     "gsg_rk_final_dev": (i32, [vp, i64, vp, vp, vp, f64]),
     "gsg_profile_enable": (i32, [vp, i32]),
     "gsg_profile_read": (i32, [vp, p_i64, p_f64, p_f64]),
+    "gsg_debug_stamps": (i32, [vp, vp, i32]),
+    "gsg_debug_spin": (i32, [vp, i32, i32, i32, i32, i32, i32]),
     "gsg_reconstruct": (i32, [vp, vp, vp, i64, vp]),
     "gsg_reconstruct_dev": (i32, [vp, vp, vp, i64, vp]),
     "gsg_spmv_csc": (i32, [i64, i64, vp, vp, vp, vp, vp]),

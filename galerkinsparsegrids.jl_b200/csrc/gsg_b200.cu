@@ -88,7 +88,7 @@ constexpr size_t SMEM_OPTIN_MAX = 227 * 1024;
 constexpr int SHORT_TILE_DOUBLES = 4096;
 constexpr int TMA_STAGE_TARGET_DOUBLES = 5840;
 
-enum class Kind { SHORT_TMA, SHORT, LONG, LONG2, CONSTH, GENERIC };
+enum class Kind { SHORT_TMA, LONG, LONG2, CONSTH, GENERIC };   // LONG: transient tag while a class is being placed
 
 struct SweepClass {          // one launch of a sweep
     int p = 0;               // pole length class (SHORT_TMA: the largest short class it holds)
@@ -101,10 +101,8 @@ struct SweepClass {          // one launch of a sweep
     int nbuf = 4;            // ... and record-ring depth (2 with 16 warps)
     std::vector<std::unique_ptr<DevBuf<int>>> passBlk, passRow;
     DevBuf<TileL2> l2tiles;
-    DevBuf<int> partBlk, partRow;
     size_t smem = 0;
     DevBuf<TileDev> tiles;
-    DevBuf<TileLong> ltiles;
     DevBuf<TileS> stiles;
     DevBuf<TileS2> s2tiles;     // second-generation streaming kernel
     bool stream2 = false;
@@ -134,14 +132,9 @@ struct gsg_plan {
     DevBuf<int> b_rowptr, b_col;
     DevBuf<double> b_val;
     int KK2 = 0;
-    std::vector<std::unique_ptr<DevBuf<double>>> dense;   // index p (legacy short kernel)
-    DevBuf<double> dense_all;                              // concatenated (device copy)
     std::vector<double> dense_host;                        // concatenated, passed as kernel parameter
     int hoff[5] = {0, 0, 0, 0, 0};
     int htotal = 0, short_pmax = -1;
-    // long kernel: per p, the principal sub-block as a compact stream of block records
-    std::vector<std::unique_ptr<DevBuf<unsigned char>>> lrec;   // index p
-    std::vector<std::vector<int>> lrow_start;                    // index p: first record of each block-row (+ end)
     // register-tiled long kernel: column passes.  The principal sub-block of class p is cut into
     // npass column slices (so that a 32*C-pole x tile of one slice fits shared memory); each slice is
     // its own record stream with block columns relative to the slice
@@ -189,9 +182,6 @@ struct gsg_plan {
     // multi-GPU block partition (gsg_plan_set_partition): part_bits dimensions D, D-1, ... each split the
     // multi-level blocks into {level == 0} and {level >= 1}; rank bit j = 1 owns level_{D-j} == 0
     int part_rank = 0, part_bits = 0;
-
-    // multi-GPU work sharing: this process launches tiles [rank*nt/nranks, (rank+1)*nt/nranks)
-    int shard_rank = 0, shard_n = 1;
 
     // optional timing of the dominant (streaming) kernel with CUDA events on its stream
     bool prof_on = false;
@@ -265,45 +255,6 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     GSG_TRY(P.b_col.upload(col));
     GSG_TRY(P.b_val.upload(val));
 
-    // long kernel: per p the principal sub-block (rows and columns < 2^p) as a stream of block
-    // records {K*K values row-major, int col, int flags (bit 0 = last record of its block-row)};
-    // every row owns at least one record so the end-of-row flag always exists
-    P.lrec.resize(n + 1);
-    P.lrow_start.assign(n + 1, {});
-    {
-        const int KK = K * K;
-        const int REC = (KK * 8 + 8 + 15) & ~15;
-        for (int p = 0; p <= n; ++p) {
-            const int nq = 1 << p;
-            std::vector<unsigned char> buf;
-            std::vector<int>& rs = P.lrow_start[p];
-            rs.assign(nq + 1, 0);
-            int nrec = 0;
-            for (int q = 0; q < nq; ++q) {
-                rs[q] = nrec;
-                int cnt = 0;
-                for (int b = rowptr[q]; b < rowptr[q + 1] && col[b] < nq; ++b) ++cnt;
-                const int emit = std::max(cnt, 1);
-                for (int i = 0; i < emit; ++i) {
-                    buf.resize((size_t)(nrec + 1) * REC, 0);
-                    unsigned char* rec = buf.data() + (size_t)nrec * REC;
-                    int meta[2] = {0, i == emit - 1 ? 1 : 0};
-                    if (i < cnt) {
-                        const int b = rowptr[q] + i;
-                        std::memcpy(rec, val.data() + (size_t)b * P.KK2, (size_t)KK * 8);
-                        meta[0] = col[b];
-                    }
-                    std::memcpy(rec + KK * 8, meta, 8);
-                    ++nrec;
-                }
-            }
-            rs[nq] = nrec;
-            buf.resize((size_t)(nrec + 2 * LONG_CH) * REC, 0);     // over-read slack for whole-chunk copies
-            P.lrec[p].reset(new DevBuf<unsigned char>());
-            GSG_TRY(P.lrec[p]->upload(buf));
-        }
-    }
-
     // constant-bank kernel (k = 3, N' = 48 and 96): the stored blocks must lie inside the structural
     // pattern the kernel was unrolled for; otherwise that class falls back to the register-tiled kernel
     P.consth_vals.assign(n + 1, {});
@@ -333,7 +284,6 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     }
 
     // dense principal sub-blocks for the register-resident short classes
-    P.dense.resize(n + 1);
     std::vector<double> all;
     for (int p = 0; p <= n && p <= SHORT_MAX_P; ++p) {
         const int NP = K << p;
@@ -341,8 +291,6 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         std::vector<double> d((size_t)NP * NP);
         for (int i = 0; i < NP; ++i)
             for (int j = 0; j < NP; ++j) d[(size_t)i * NP + j] = Hd[(size_t)i * N1 + j];
-        P.dense[p].reset(new DevBuf<double>());
-        GSG_TRY(P.dense[p]->upload(d));
         P.hoff[p] = (int)all.size();
         all.insert(all.end(), d.begin(), d.end());
         if (all.size() & 1) all.push_back(0.0);
@@ -350,7 +298,6 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
     }
     P.htotal = (int)all.size();
     P.dense_host = all;
-    GSG_TRY(P.dense_all.upload(all));
     return 0;
 }
 
@@ -405,7 +352,6 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
     dir.A = pow_int(K, d);
     const int KD = (int)S.kD, KDp = (int)S.kDp;
     const int PI = KD / K;
-    const bool legacy_short = getenv("GSG_SHORT_LEGACY") != nullptr;
 
     // groups keyed by the other dims' levels, in layout order of their level_d = 0 block
     std::vector<GroupDev> groups;
@@ -452,7 +398,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
     GSG_TRY(dir.groups.upload(groups));
 
     // ---- merged TMA class for all register-resident pole lengths
-    const bool use_tma = !legacy_short && P.short_pmax >= 0 && K <= 5;
+    const bool use_tma = P.short_pmax >= 0 && K <= 5;
     if (use_tma) {
         SweepClass c;
         c.kind = Kind::SHORT_TMA;
@@ -549,20 +495,10 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
         const int REC = (K * K * 8 + 8 + 15) & ~15;
-        const size_t warp_bytes = (size_t)LONG_NBUF * LONG_CH * REC + (size_t)K * 32 * 8;
-        int nw = NQ >= 64 ? 16 : (NQ >= 16 ? 8 : 4);
-        const int nr_long = PI >= 32 ? 1 : 32 / PI;
-        const size_t tile_bytes = (size_t)NP * 32 * 8 + (((size_t)NQ * nr_long * 8 + 15) & ~(size_t)15);  // x tile + cell offsets
-        while (nw > 2 && tile_bytes + nw * warp_bytes + 2048 > SMEM_OPTIN_MAX) nw -= (nw > 8 ? 4 : nw / 2);
-        const size_t long_smem = tile_bytes + nw * warp_bytes;
-        if (short_supported(K, p)) {
-            if (tma_active) continue;
-            c.kind = Kind::SHORT;
-        } else if (K <= 5 && long_smem + 2048 <= SMEM_OPTIN_MAX) {
-            c.kind = Kind::LONG;
-        } else {
-            c.kind = Kind::GENERIC;
-        }
+        if (short_supported(K, p) && tma_active) continue;        // served by the streaming class above
+        // register-tiled / constant-bank kernels for the long classes of k <= 5; everything else (k > 5, short
+        // classes whose stage does not fit shared memory) goes to the generic block-CSR kernel
+        c.kind = (K <= 5 && !short_supported(K, p)) ? Kind::LONG : Kind::GENERIC;
         if (c.kind == Kind::LONG && K == 3 && (p == 4 || p == 5) && !P.consth_vals[p].empty()) {
             // constant-bank kernel: one warp per 32 consecutive (flattened) poles of one group
             std::vector<TileL2> tl2;
@@ -600,7 +536,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
             dir.classes.push_back(std::move(c));
             continue;
         }
-        if (c.kind == Kind::LONG && !getenv("GSG_LONG_V1")) {
+        if (c.kind == Kind::LONG) {
             // register-tiled long kernel: tiles of 32*C consecutive (flattened) poles of one group
             long long maxpoles = 0, ngrp = 0;
             for (size_t gi = 0; gi < groups.size(); ++gi)
@@ -721,77 +657,9 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
                 continue;
             }
         }
-        if (c.kind == Kind::LONG) {
-            std::vector<TileLong> ll;
-            c.nwarps = nw;
-            c.smem = long_smem;
-            const int A = dir.A, B = PI / A;
-            for (size_t gi = 0; gi < groups.size(); ++gi) {
-                if (groups[gi].p != p) continue;
-                if (PI >= 32) {
-                    for (int r = 0; r < groups[gi].nitems; ++r) {
-                        if (A >= 32) {
-                            for (int b = 0; b < B; ++b)
-                                for (int a0 = 0; a0 < A; a0 += 32)
-                                    ll.push_back(TileLong{(int)gi, r, a0 + K * A * b, 1, (short)std::min(32, A - a0), 1, 0});
-                        } else {
-                            const int nbmax = 32 / A;
-                            for (int b0 = 0; b0 < B; b0 += nbmax)
-                                ll.push_back(TileLong{(int)gi, r, K * A * b0, 1, (short)A, (short)std::min(nbmax, B - b0), 0});
-                        }
-                    }
-                } else {
-                    const int nrmax = 32 / PI;
-                    for (int r0 = 0; r0 < groups[gi].nitems; r0 += nrmax)
-                        ll.push_back(TileLong{(int)gi, r0, 0, (short)std::min(nrmax, groups[gi].nitems - r0), (short)A, (short)B, 0});
-                }
-            }
-            if (ll.empty()) continue;
-            // row parts: enough CTAs to cover the GPU twice, but at least ~32 records per warp
-            const std::vector<int>& rs = P.lrow_start[p];
-            const int nrec = rs[NQ];
-            // row parts: one CTA per pole set is enough (its warps stream ~nrec/nw records each from
-            // the cp.async ring); only split when a class would otherwise occupy fewer than 16 SMs
-            int rsplit = 1;
-            if (const char* e = getenv("GSG_LONG_RSPLIT")) rsplit = atoi(e);
-            else if ((long long)ll.size() < 16) rsplit = (int)std::min<long long>(16 / (long long)ll.size(), std::max(1, nrec / (nw * 64)));
-            rsplit = std::max(1, std::min(rsplit, 64));
-            c.rsplit = rsplit;
-            const int G = rsplit * nw;
-            std::vector<int> pb(G + 1, nrec), pr(G + 1, NQ);
-            pb[0] = 0; pr[0] = 0;
-            {
-                const long long total = (long long)nrec + NQ;       // +1 per row: epilogue cost
-                int q = 0;
-                for (int g = 1; g < G; ++g) {
-                    const long long target = total * g / G;
-                    while (q < NQ && (long long)rs[q] + q < target) ++q;
-                    pr[g] = std::max(q, pr[g - 1]);
-                    pb[g] = rs[pr[g]];
-                }
-            }
-            GSG_TRY(c.partBlk.upload(pb));
-            GSG_TRY(c.partRow.upload(pr));
-            std::vector<TileLong> full;
-            full.reserve(ll.size() * rsplit);
-            for (int part = 0; part < rsplit; ++part)       // coarse (long) rows first
-                for (TileLong tl1 : ll) { tl1.part = (short)part; full.push_back(tl1); }
-            c.ntiles = (int)full.size();
-            GSG_TRY(c.ltiles.upload(full));
-            dir.classes.push_back(std::move(c));
-            continue;
-        }
+        c.kind = Kind::GENERIC;               // no register-tiled configuration fits: generic kernel
         std::vector<TileDev> tl;
-        if (c.kind == Kind::SHORT) {
-            int nr_max = std::max(1, SHORT_TILE_DOUBLES / (NQ * KD));
-            c.NPOLE = PI;
-            for (size_t gi = 0; gi < groups.size(); ++gi) {
-                if (groups[gi].p != p) continue;
-                for (int r0 = 0; r0 < groups[gi].nitems; r0 += nr_max)
-                    tl.push_back(TileDev{(int)gi, r0, std::min(nr_max, groups[gi].nitems - r0), 0});
-            }
-            c.smem = ((size_t)((NP * NP + 1) & ~1) + (size_t)NQ * nr_max * KD) * sizeof(double);
-        } else {
+        {
             // largest power-of-K pole sub-range that fits the budget
             int npole = 1;
             if (K >= 2)
@@ -984,11 +852,10 @@ int build_pairs(gsg_plan& P) {
     return 0;
 }
 
-// tile range of this process (multi-GPU work sharing)
-inline void tile_range(const gsg_plan& pl, int ntiles, int& begin, int& count) {
-    begin = (int)((long long)ntiles * pl.shard_rank / pl.shard_n);
-    const int end = (int)((long long)ntiles * (pl.shard_rank + 1) / pl.shard_n);
-    count = end - begin;
+// tile range of a launch (every launch covers its whole tile list)
+inline void tile_range(const gsg_plan&, int ntiles, int& begin, int& count) {
+    begin = 0;
+    count = ntiles;
 }
 
 int launch_check(const char* what, int K, const SweepClass& c) {
@@ -1101,53 +968,6 @@ int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y
     return fail(GSG_ERR_UNSUPPORTED, "internal: pair kernel not instantiated");
 }
 
-template <int K, int P>
-int launch_short_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
-                    double* y, double alpha, double beta) {
-    auto kern = sweep_short_kernel<K, P>;
-    static thread_local size_t configured = 0;
-    GSG_TRY(ensure_smem(kern, c.smem, configured));
-    int tb, tn;
-    tile_range(pl, c.ntiles, tb, tn);
-    if (tn == 0) return 0;
-    kern<<<tn, 256, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.tiles.p + tb, pl.dense[P]->p, (int)pl.S.kD,
-                                   (int)pl.S.kDp, dir.A);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_check("sweep_short", K, c);
-}
-
-template <int K>
-int launch_short_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
-                   double* y, double alpha, double beta) {
-    if constexpr (K >= 1 && K <= 5) {
-        switch (c.p) {
-            case 0: return launch_short_kp<K, 0>(pl, st, dir, c, x, y, alpha, beta);
-            case 1: if constexpr ((K << 1) <= SHORT_MAX_NP) return launch_short_kp<K, 1>(pl, st, dir, c, x, y, alpha, beta); break;
-            case 2: if constexpr ((K << 2) <= SHORT_MAX_NP) return launch_short_kp<K, 2>(pl, st, dir, c, x, y, alpha, beta); break;
-            case 3: if constexpr ((K << 3) <= SHORT_MAX_NP) return launch_short_kp<K, 3>(pl, st, dir, c, x, y, alpha, beta); break;
-        }
-    }
-    return fail(GSG_ERR_UNSUPPORTED, "internal: short class not instantiated");
-}
-
-template <int K>
-int launch_long_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
-                  double* y, double alpha, double beta) {
-    if constexpr (K >= 1 && K <= 5) {
-        auto kern = sweep_long_kernel<K>;
-        static thread_local size_t configured = 0;
-        GSG_TRY(ensure_smem(kern, c.smem, configured));
-        int tb, tn;
-        tile_range(pl, c.ntiles, tb, tn);
-        if (tn == 0) return 0;
-        kern<<<tn, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta, dir.groups.p, c.ltiles.p + tb, pl.lrec[c.p]->p,
-                                                 c.partBlk.p, c.partRow.p, c.p, (int)pl.S.kDp, dir.A);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        return launch_check("sweep_long", K, c);
-    }
-    return fail(GSG_ERR_UNSUPPORTED, "internal: long kernel not instantiated");
-}
-
 template <int K, int C, int NB>
 int launch_long2_kc(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                     double* y, double alpha, double beta) {
@@ -1253,8 +1073,6 @@ int launch_class(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swee
     const int K = pl.S.k;
     switch (c.kind) {
         case Kind::SHORT_TMA: GSG_K_SWITCH(launch_short_tma, pl, st, dir, c, x, y, alpha, beta); break;
-        case Kind::SHORT: GSG_K_SWITCH(launch_short_k, pl, st, dir, c, x, y, alpha, beta); break;
-        case Kind::LONG: GSG_K_SWITCH(launch_long_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::LONG2: GSG_K_SWITCH(launch_long2_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::CONSTH: return launch_consth(pl, st, dir, c, x, y, alpha, beta);
         case Kind::GENERIC:
@@ -1550,7 +1368,9 @@ static int check_dkn(int D, int k, int n, int scheme) {
 int gsg_get_size(int D, int k, int n, int scheme, int64_t* size_out) {
     GSG_TRY(check_dkn(D, k, n, scheme));
     if (!size_out) return fail(GSG_ERR_ARG, "null output");
-    *size_out = gsg::get_size(D, k, n, scheme);
+    const int64_t N = gsg::get_size(D, k, n, scheme);
+    if (N < 0) return fail(GSG_ERR_UNSUPPORTED, "index set too large (more than 4e6 multi-levels or 2^40 DOFs)");
+    *size_out = N;
     return 0;
 }
 
@@ -1607,7 +1427,7 @@ int gsg_tensor_construct(int D, int k, int n, int scheme, const double* const* v
     GSG_TRY(check_dkn(D, k, n, scheme));
     if (!vcoeffs_1d || !out) return fail(GSG_ERR_ARG, "null pointer");
     gsg::IndexSet S;
-    S.build(D, k, n, scheme);
+    if (!S.build(D, k, n, scheme)) return fail(GSG_ERR_UNSUPPORTED, "index set too large");
     gsg::tensor_construct(S, vcoeffs_1d, out);
     return 0;
 }
@@ -1635,8 +1455,14 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
     GSG_CUDA(cudaSetDevice(device));
     std::unique_ptr<gsg_plan> P(new gsg_plan());
     P->device = device;
-    P->S.build(D, k, n, scheme);
-    if (P->S.kD > (1 << 20)) return fail(GSG_ERR_UNSUPPORTED, "k^D too large");
+    {   // size guards BEFORE the index set is enumerated
+        double kd = 1.0;
+        for (int i = 0; i < D; ++i) kd *= k;
+        if (kd > (double)(1 << 20)) return fail(GSG_ERR_UNSUPPORTED, "k^D too large");
+        if (((int64_t)k << n) > 16384) return fail(GSG_ERR_UNSUPPORTED, "k*2^n > 16384 not supported");
+    }
+    if (!P->S.build(D, k, n, scheme)) return fail(GSG_ERR_UNSUPPORTED, "index set too large (more than 4e6 multi-levels or 2^40 DOFs)");
+    if (P->S.Npad / P->S.kDp > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many multi-cells");
     cudaDeviceProp prop;
     GSG_CUDA(cudaGetDeviceProperties(&prop, device));
     P->sm_count = prop.multiProcessorCount;
@@ -1742,8 +1568,8 @@ int gsg_plan_set_partition(gsg_plan* plan, int rank, int nranks) {
     GSG_TRY(check_plan(plan));
     int bits = 0;
     while ((1 << bits) < nranks) ++bits;
-    if (nranks < 1 || (1 << bits) != nranks || bits > plan->S.D || rank < 0 || rank >= nranks)
-        return fail(GSG_ERR_ARG, "partition: nranks must be a power of two <= 2^D and 0 <= rank < nranks");
+    if (nranks < 1 || (1 << bits) != nranks || (bits > 0 && bits >= plan->S.D) || rank < 0 || rank >= nranks)
+        return fail(GSG_ERR_ARG, "partition: nranks must be a power of two < 2^D (one direction stays local) and 0 <= rank < nranks");
     GSG_CUDA(cudaStreamSynchronize(plan->stream));
     plan->part_rank = rank;
     plan->part_bits = bits;
@@ -1822,13 +1648,6 @@ int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncell
                                                             c2, c3, c4);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GSG_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int gsg_plan_set_shard(gsg_plan* plan, int rank, int nranks) {
-    if (!plan || nranks < 1 || rank < 0 || rank >= nranks) return fail(GSG_ERR_ARG, "bad shard");
-    plan->shard_rank = rank;
-    plan->shard_n = nranks;
     return 0;
 }
 
@@ -1949,6 +1768,8 @@ int gsg_apply_dirs_dev(gsg_plan* plan, const double* c, unsigned dmask, double b
 int gsg_apply_laplacian_dev(gsg_plan* plan, const double* x_dev, double* y_dev, double* tmp_dev) {
     GSG_TRY(check_plan(plan));
     if (!x_dev || !y_dev || !tmp_dev) return fail(GSG_ERR_ARG, "bad pointers");
+    if (x_dev == y_dev || x_dev == tmp_dev || y_dev == tmp_dev)
+        return fail(GSG_ERR_ARG, "x, y and tmp must be three distinct device vectors");
     return laplacian(*plan, x_dev, y_dev, tmp_dev);
 }
 
@@ -2139,6 +1960,11 @@ int gsg_reconstruct(gsg_plan* plan, const double* vcoeffs, const double* points,
     if (!vcoeffs || !points || !out || npts < 0) return fail(GSG_ERR_ARG, "bad argument");
     if (npts == 0) return 0;
     gsg_plan& pl = *plan;
+    // the reference indexes coeffs[key][cell] with cell = 1 + floor(2^(l-1) x): a point outside [0, 1] (or NaN)
+    // is a BoundsError there (src/dg_methods.jl:158-159)
+    for (int64_t i = 0; i < npts * pl.S.D; ++i)
+        if (!(points[i] >= 0.0 && points[i] <= 1.0))
+            return fail(GSG_ERR_ARG, "BoundsError: reconstruct point outside [0, 1]^D (point " + std::to_string(i / pl.S.D) + ")");
     GSG_TRY(pl.wx.resize((size_t)pl.S.Npad));
     GSG_TRY(pl.wpts.resize((size_t)npts * pl.S.D));
     GSG_TRY(pl.wout.resize((size_t)npts));

@@ -408,10 +408,11 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
     std::vector<int> lv(D, 0);
     int64_t off = 0, poff = 0;
     ncells_total = 0;
+    N = 0;
+    Npad = 0;
+    int sum = 0;
     while (true) {
-        int sum = 0;
-        for (int i = 0; i < D; ++i) sum += lv[i];
-        if (scheme == 1 || sum <= n) {
+        {
             Block b;
             b.level = lv;
             b.cells.resize(D);
@@ -427,9 +428,20 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
             ncells_total += b.ncells;
             by_level[lv] = (int)blocks.size();
             blocks.push_back(std::move(b));
+            if ((int64_t)blocks.size() > MAX_BLOCKS || off > MAX_DOFS) return false;   // refuse absurd sizes early
         }
-        int i = 0;  // first dimension fastest (Julia CartesianIndices order)
-        while (i < D && ++lv[i] > n) lv[i++] = 0;
+        // first dimension fastest (Julia CartesianIndices order).  Sparse scheme: only tuples with sum <= n
+        // are visited -- once ++lv[i] (all lower dimensions already reset to 0) breaks the cutoff, every larger
+        // lv[i] does too, so the odometer carries; the visiting order of the kept tuples is unchanged.
+        int i = 0;
+        while (i < D) {
+            ++lv[i];
+            ++sum;
+            if (lv[i] <= n && (scheme == 1 || sum <= n)) break;
+            sum -= lv[i];
+            lv[i] = 0;
+            ++i;
+        }
         if (i == D) break;
     }
     N = off;
@@ -439,7 +451,7 @@ bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
 
 int64_t get_size(int D, int k, int n, int scheme) {
     IndexSet S;
-    S.build(D, k, n, scheme);
+    if (!S.build(D, k, n, scheme)) return -1;
     return S.N;
 }
 

@@ -13,6 +13,8 @@ namespace gsg {
 
 constexpr int K_MAX = 10;        // src/1d_dg_functions.jl:7
 constexpr int N_MAX_LEVEL = 16;  // library limit on n
+constexpr int64_t MAX_BLOCKS = 4000000;            // library limits on the index set (IndexSet::build fails beyond)
+constexpr int64_t MAX_DOFS = int64_t(1) << 40;
 
 struct Csc {                      // 0-based compressed sparse column
     int64_t m = 0, n = 0;

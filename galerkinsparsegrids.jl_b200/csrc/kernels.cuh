@@ -19,7 +19,7 @@
 //                                             pass for both directions of a pair over 2-D sub-planes (n' <= 2)
 //   sweep_consth_kernel<K, P>      N' = 48    matrix unrolled into constant-bank operands (structural pattern)
 //   sweep_long2_kernel<K, C, NB>   N' >= 96   register-tiled: lanes = poles, C poles per lane, record stream
-//   sweep_short_tma_kernel, sweep_short_kernel, sweep_long_kernel, sweep_generic_kernel   first generation / fallbacks
+//   sweep_short_tma_kernel (small k^D: many multi-cells per tile), sweep_generic_kernel (any k <= 10, any length)
 //   rk_stage_kernel, rk_final_kernel, rk4_taylor_kernel(_cells)   RK4 updates
 //   reconstruct2_kernel (reconstruct_kernel)   batched reconstruct_DG;   spmv_csr_kernel   cross-check SpMV
 #pragma once
@@ -65,95 +65,6 @@ __device__ __forceinline__ long long cell_addr(const long long* base, int S, int
     q_decode(q, ld, cd, Cd);
     const int lo = r % S, hi = r / S;
     return base[ld] + (long long)KDp * (lo + (long long)S * (cd + (long long)Cd * hi));
-}
-
-// ------------------------------------------------------------------------------------------
-// Short poles: N' = K << P <= 32.  One CTA stages whole items (every 1-D cell's KD-double
-// multi-cell, coalesced) in shared memory, one thread owns one pole, holds it in registers,
-// multiplies by the dense N' x N' block broadcast from shared memory, writes back in place.
-// ------------------------------------------------------------------------------------------
-template <int K, int P>
-__global__ void __launch_bounds__(256)
-sweep_short_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
-                   const GroupDev* __restrict__ groups, const TileDev* __restrict__ tiles,
-                   const double* __restrict__ Mdense, int KD, int KDp, int A) {
-    constexpr int NQ = 1 << P, NP = K * NQ;
-    extern __shared__ __align__(16) double smem[];
-    double* Hs = smem;                                   // NP*NP (padded to even)
-    double* xs = smem + ((NP * NP + 1) & ~1);            // NQ * nr * KD
-    __shared__ long long sbase[MAXL + 1];
-    __shared__ int sS;
-
-    const TileDev t = tiles[blockIdx.x];
-    const int tid = threadIdx.x, nth = blockDim.x;
-    if (tid <= P) sbase[tid] = groups[t.group].base[tid];
-    if (tid == 0) sS = groups[t.group].S;
-    for (int i = tid; i < NP * NP; i += nth) Hs[i] = Mdense[i];
-    __syncthreads();
-    const int S = sS;
-    const int nr = t.nr;
-    const int ncell = NQ * nr;
-    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
-
-    // ---- stage in: one warp per multi-cell, lanes stride the KD contiguous doubles
-    for (int c = warp; c < ncell; c += nwarp) {
-        const int q = c / nr, r = c - q * nr;
-        const double* src = X + cell_addr(sbase, S, q, t.r0 + r, KDp);
-        double* dst = xs + (size_t)c * KD;
-        int e = lane;
-        for (; e + 96 < KD; e += 128) {
-            const double v0 = src[e], v1 = src[e + 32], v2 = src[e + 64], v3 = src[e + 96];
-            dst[e] = v0; dst[e + 32] = v1; dst[e + 64] = v2; dst[e + 96] = v3;
-        }
-        for (; e < KD; e += 32) dst[e] = src[e];
-    }
-    __syncthreads();
-
-    // ---- compute: thread per pole
-    const int PI = KD / K;            // poles per item
-    const int npole = nr * PI;
-    const int KA = K * A;
-    for (int pj = tid; pj < npole; pj += nth) {
-        const int r = pj / PI, j = pj - r * PI;
-        const int b = j / A, a = j - b * A;
-        double* pole = xs + (size_t)r * KD + a + KA * b;     // + q*nr*KD + A*m
-        double x[NP];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-#pragma unroll
-            for (int m = 0; m < K; ++m) x[q * K + m] = pole[(size_t)q * nr * KD + A * m];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-#pragma unroll
-            for (int m = 0; m < K; ++m) {
-                const int i = q * K + m;
-                double acc = 0.0;
-#pragma unroll
-                for (int jx = 0; jx < NP; ++jx) acc = fma(Hs[i * NP + jx], x[jx], acc);
-                pole[(size_t)q * nr * KD + A * m] = acc;
-            }
-    }
-    __syncthreads();
-
-    // ---- stage out with the epilogue y = alpha*Mx + beta*y
-    for (int c = warp; c < ncell; c += nwarp) {
-        const int q = c / nr, r = c - q * nr;
-        double* dstg = Y + cell_addr(sbase, S, q, t.r0 + r, KDp);
-        const double* srcs = xs + (size_t)c * KD;
-        if (beta == 0.0) {
-            for (int e = lane; e < KD; e += 32) dstg[e] = alpha * srcs[e];
-        } else {
-            int e = lane;
-            for (; e + 96 < KD; e += 128) {
-                const double y0 = dstg[e], y1 = dstg[e + 32], y2 = dstg[e + 64], y3 = dstg[e + 96];
-                dstg[e] = fma(alpha, srcs[e], beta * y0);
-                dstg[e + 32] = fma(alpha, srcs[e + 32], beta * y1);
-                dstg[e + 64] = fma(alpha, srcs[e + 64], beta * y2);
-                dstg[e + 96] = fma(alpha, srcs[e + 96], beta * y3);
-            }
-            for (; e < KD; e += 32) dstg[e] = fma(alpha, srcs[e], beta * dstg[e]);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -932,25 +843,8 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// Long poles (p >= 4 at k = 3): lanes = poles.  A tile holds PT <= 32 poles (a sub-range
-// a0..a0+na x b0..b0+nb of one item's poles, or nr whole items when an item has few poles) and
-// one ROW PART of the principal sub-block; the whole x tile sits in shared memory as xs[row][32]
-// (conflict-free for lanes = poles).  The matrix of class p is a compact stream of K x K block
-// records (values, block column, end-of-row flag) in row order.  Every warp owns a contiguous
-// range of whole block-rows (host partition balanced in block count) and streams its records
-// through a private 3-deep cp.async ring in shared memory, so no L2 latency is exposed in the
-// inner loop: per record 5 broadcast LDS.128 + K conflict-free LDS.64 of x + K*K DFMAs.  Each
-// finished block-row goes through a per-warp scratch so the global write is coalesced.
-//   in-item order t -> a = t % na, m = (t / na) % K, bl = t / (K*na):
-//   pole = a + na*bl, in-cell offset = ebase + a + A*m + K*A*bl.
+// Long poles: record stream helpers
 // ------------------------------------------------------------------------------------------
-struct TileLong {
-    int group;
-    int r0;
-    int ebase;
-    short nr, na, nb, part;   // part: which row part of the matrix this CTA computes
-};
-
 constexpr int LONG_CH = 8;      // records per ring chunk
 constexpr int LONG_NBUF = 4;    // ring depth
 
@@ -970,141 +864,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K>
-__global__ void __launch_bounds__(512)
-sweep_long_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, double beta,
-                  const GroupDev* __restrict__ groups, const TileLong* __restrict__ tiles,
-                  const unsigned char* __restrict__ recs, const int* __restrict__ partBlk,
-                  const int* __restrict__ partRow, int p, int KDp, int A) {
-    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
-    constexpr int CHB = LONG_CH * REC;                        // bytes per ring chunk
-    constexpr int WARP_BYTES = LONG_NBUF * CHB + K * 32 * 8;  // ring + scratch per warp
-    const int NQ = 1 << p, NP = K * NQ;
-    extern __shared__ __align__(128) unsigned char smraw[];
-    __shared__ long long sbase[MAXL + 1];
-    __shared__ int sS;
-    __shared__ short tab_row[K * 32];   // m*32 + pole-in-item
-    __shared__ int tab_g[K * 32];       // in-cell offset
-
-    const TileLong t = tiles[blockIdx.x];
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, nwarp = nth >> 5;
-    const int na = t.na, nb = t.nb, nr = t.nr;
-    const int PIt = na * nb;            // poles per item in this tile
-    const int PT = nr * PIt;            // poles in the tile (<= 32)
-    const int TL = K * PIt;
-    double* xs = reinterpret_cast<double*>(smraw);                                  // NP * 32
-    long long* caddr = reinterpret_cast<long long*>(smraw + (size_t)NP * 32 * 8);   // NQ * nr cell offsets
-    const int caddr_bytes = (NQ * nr * 8 + 15) & ~15;
-    unsigned char* wbase = smraw + (size_t)NP * 32 * 8 + caddr_bytes + (size_t)warp * WARP_BYTES;
-    unsigned char* ring = wbase;
-    double* scratch = reinterpret_cast<double*>(wbase + LONG_NBUF * CHB);
-
-    // this warp's records [b0, b1) and first block-row q
-    const int gpart = t.part * nwarp + warp;
-    const int b0 = partBlk[gpart], b1 = partBlk[gpart + 1];
-    int q = partRow[gpart];
-    const int c_first = b0 / LONG_CH, c_last = b1 > b0 ? (b1 - 1) / LONG_CH : c_first - 1;
-
-    auto issue_chunk = [&](int c) {
-        if (c <= c_last) {
-            const unsigned char* src = recs + (size_t)c * CHB;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (c % LONG_NBUF) * CHB);
-            for (int g = lane; g < CHB / 16; g += 32) cp_async16(dst + g * 16, src + g * 16);
-        }
-        cp_async_commit();
-    };
-
-    if (tid <= p) sbase[tid] = groups[t.group].base[tid];
-    if (tid == 0) sS = groups[t.group].S;
-    for (int tt = tid; tt < TL; tt += nth) {
-        const int a = tt % na, rest = tt / na;
-        const int m = rest % K, bl = rest / K;
-        tab_row[tt] = (short)(m * 32 + a + na * bl);
-        tab_g[tt] = t.ebase + a + A * m + K * A * bl;
-    }
-    issue_chunk(c_first);
-    issue_chunk(c_first + 1);
-    issue_chunk(c_first + 2);
-    __syncthreads();
-    const int S = sS;
-    const int ncell = NQ * nr;
-    for (int c = tid; c < ncell; c += nth) {
-        const int qq = c / nr, r = c - qq * nr;
-        caddr[c] = cell_addr(sbase, S, qq, t.r0 + r, KDp);
-    }
-    __syncthreads();
-
-    // ---- stage the x tile in (asynchronous 8-byte copies, transposed to xs[row][pole])
-    for (int c = warp; c < ncell; c += nwarp) {
-        const int qq = c / nr, r = c - qq * nr;
-        const double* src = X + caddr[c];
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + (size_t)qq * K * 32 + r * PIt);
-        for (int tt = lane; tt < TL; tt += 32) cp_async8(dst + tab_row[tt] * 8, src + tab_g[tt]);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // ---- stream this warp's block records
-    const bool active = lane < PT;
-    double acc[K];
-#pragma unroll
-    for (int m = 0; m < K; ++m) acc[m] = 0.0;
-    for (int c = c_first; c <= c_last; ++c) {
-        issue_chunk(c + 3);
-        cp_async_wait<3>();            // chunk c has landed (this thread's copies) ...
-        __syncwarp();                  // ... and every lane's
-        const unsigned char* buf = ring + (c % LONG_NBUF) * CHB;
-        const int lo = max(b0, c * LONG_CH) - c * LONG_CH, hi = min(b1, (c + 1) * LONG_CH) - c * LONG_CH;
-        for (int i = lo; i < hi; ++i) {
-            const unsigned char* rec = buf + i * REC;
-            const int2 meta = *reinterpret_cast<const int2*>(rec + KK * 8);
-            const double* hv = reinterpret_cast<const double*>(rec);
-            const double* xv = xs + (size_t)meta.x * K * 32 + lane;
-            double xr[K];
-#pragma unroll
-            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[mi * 32];
-#pragma unroll
-            for (int mo = 0; mo < K; ++mo)
-#pragma unroll
-                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(hv[mo * K + mi], xr[mi], acc[mo]);
-            if (meta.y & 1) {          // end of block-row q: coalesced write through the scratch
-                __syncwarp();
-                if (active) {
-#pragma unroll
-                    for (int m = 0; m < K; ++m) scratch[m * 32 + lane] = acc[m];
-                }
-                __syncwarp();
-                for (int r = 0; r < nr; ++r) {
-                    double* dstg = Y + caddr[q * nr + r];
-                    const double* sc = scratch + r * PIt;
-                    if (beta == 0.0) {
-                        for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * sc[tab_row[tt]];
-                    } else {
-                        for (int tt = lane; tt < TL; tt += 32) {
-                            const int g = tab_g[tt];
-                            dstg[g] = fma(alpha, sc[tab_row[tt]], beta * dstg[g]);
-                        }
-                    }
-                }
-                ++q;
-#pragma unroll
-                for (int m = 0; m < K; ++m) acc[m] = 0.0;
-            }
-        }
-        __syncwarp();                  // the chunk buffer is refilled by the next iteration's issue
-    }
-    cp_async_wait<0>();
-}
-
 // ------------------------------------------------------------------------------------------
 // Long poles, register-tiled (the shipped path for N' > 32): lanes = poles, C poles per lane.
 // A CTA tile holds PT = 32*C consecutive poles of one pole group (flattened pole index
 // item * PI + j, so a tile may straddle items) and one ROW PART of the principal sub-block; the
 // whole x tile sits in shared memory as xs[row][PT] (conflict-free for lanes = poles).  Every
 // warp owns a contiguous range of whole block-rows and streams its K x K block records through
-// a private cp.async ring (same record stream as sweep_long_kernel).  Per record a lane loads
+// a private cp.async ring (compact record stream per class).  Per record a lane loads
 // the K*K uniform H values once (broadcast LDS) and K*C of its own x values and issues K*K*C
 // DFMAs: shared-memory wavefronts per DFMA fall from 2.9 (C = 1) to 1.2 (C = 4) -- shared-memory
 // delivery, not the fp64 pipe, is what bounds this kernel.
@@ -1656,6 +1422,17 @@ reconstruct_kernel(ReconTables T, const double* __restrict__ coeffs, const doubl
 
     for (long long pt = (long long)blockIdx.x * nwarp + warp; pt < npts; pt += (long long)gridDim.x * nwarp) {
         __syncwarp();
+        {   // a point outside [0, 1]^D (or NaN) is a BoundsError in the reference: flag it, never dereference
+            bool bad = false;
+            for (int d = lane; d < D; d += 32) {
+                const double xd = pts[pt * D + d];
+                bad = bad || !(xd >= 0.0 && xd <= 1.0);
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) out[pt] = __longlong_as_double(0x7ff8000000000000LL);
+                continue;
+            }
+        }
         for (int idx = lane; idx < ntab; idx += 32) {
             const int m = idx % k, dl = idx / k, l = dl % n1, d = dl / n1;
             const double x = pts[pt * D + d];
@@ -1744,6 +1521,17 @@ reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const doub
 
     for (long long pt = (long long)blockIdx.x * nwarp + warp; pt < npts; pt += (long long)gridDim.x * nwarp) {
         __syncwarp();
+        {   // a point outside [0, 1]^D (or NaN) is a BoundsError in the reference: flag it, never dereference
+            bool bad = false;
+            for (int d = lane; d < D; d += 32) {
+                const double xd = pts[pt * D + d];
+                bad = bad || !(xd >= 0.0 && xd <= 1.0);
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) out[pt] = __longlong_as_double(0x7ff8000000000000LL);
+                continue;
+            }
+        }
         for (int idx = lane; idx < ntab; idx += 32) {
             const int m = idx % k, dl = idx / k, l = dl % n1, d = dl / n1;
             const double x = pts[pt * D + d];

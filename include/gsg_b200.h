@@ -148,10 +148,6 @@ int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncell
                              const double* v2, const double* v3, const double* v4, double c1, double c2, double c3,
                              double c4);
 
-/* Multi-GPU work sharing: after set_shard(rank, nranks) every sweep of this plan launches only
- * this rank's contiguous slice of each tile list, i.e. it ACCUMULATES a partial operator result
- * (the slices of all ranks sum to the full result; use beta = 1 into a zeroed vector). */
-int gsg_plan_set_shard(gsg_plan* plan, int rank, int nranks);
 /* w = u + cw*k ; acc = (first ? u : acc) + ca*k   on `len` entries (any sub-range) */
 int gsg_rk_stage_dev(gsg_plan* plan, int64_t len, const double* u, const double* k, double* acc,
                      double* w, double cw, double ca, int first);
@@ -165,12 +161,19 @@ int gsg_rk_final_dev(gsg_plan* plan, int64_t len, double* u, const double* k, co
 int gsg_profile_enable(gsg_plan* plan, int on);
 int gsg_profile_read(gsg_plan* plan, int64_t* launches_out, double* total_ms_out, double* dofs_out);
 
+/* development aids (tools/stamps.py, tools/placement.py): enable (first call) / read back per-phase clock
+ * stamps of the sweep kernels; launch a spinner with a chosen resource footprint */
+int gsg_debug_stamps(gsg_plan* plan, long long* out, int n);
+int gsg_debug_spin(gsg_plan* plan, int which, int grid, int threads, int smem, int ns, int slot);
+
 /* ---- batched reconstruct_DG -------------------------------------------------------------------- */
 /* out[i] = reconstruct_DG(V2D(vcoeffs), points[:, i])   src/dg_methods.jl:150-165;
  * points is a column-major D x npts matrix (Julia Matrix{Float64}).  Called once per point
  * by mcerr's loop in the reference (src/error_measure.jl:12-19,39-41). */
 int gsg_reconstruct(gsg_plan* plan, const double* vcoeffs, const double* points, int64_t npts,
                     double* out);
+/* device variant: points are not validated on the host; a point outside [0, 1]^D (a BoundsError in the
+ * reference) yields NaN in out_dev instead of an out-of-bounds read */
 int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double* points_dev,
                         int64_t npts, double* out_dev);
 

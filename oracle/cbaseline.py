@@ -41,6 +41,12 @@ def _load():
     lib.gsgo_axpy.restype = None
     lib.gsgo_axpy.argtypes = [i64, f64, vp, vp]
     lib.gsgo_max_threads.restype = C.c_int
+    lib.gsgo_set_threads.restype = None
+    lib.gsgo_set_threads.argtypes = [C.c_int]
+    lib.gsgo_apply_D_poles.restype = C.c_int
+    lib.gsgo_apply_D_poles.argtypes = [C.c_int] * 5 + [vp, vp, vp, vp, vp]
+    lib.gsgo_apply_D_assembled.restype = i64
+    lib.gsgo_apply_D_assembled.argtypes = [C.c_int] * 5 + [vp, vp, vp, vp, vp, i64]
     return lib
 
 
@@ -102,6 +108,46 @@ def D_matrix(D, d, k, n, H, scheme="sparse"):
 
 def spmv_csc(colptr, rowval, nzval, x, y):
     lib().gsgo_spmv_csc(colptr.size - 1, _p(colptr), _p(rowval), _p(nzval), _p(x), _p(y))
+
+
+def apply_D_poles(D, d, k, n, H, x, scheme="sparse"):
+    """y = D_d x, pole by pole in C (OpenMP over pole groups), per-row summation order of the CSC scatter."""
+    hc, hr, hv = _H_arrays(H)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    if lib().gsgo_apply_D_poles(D, k, n, _SCHEME[scheme], d, _p(hc), _p(hr), _p(hv), _p(x), _p(y)) != 0:
+        raise RuntimeError("gsgo_apply_D_poles failed")
+    return y
+
+
+def apply_D_assembled(D, d, k, n, H, x, scheme="sparse", slab_cols=1 << 20):
+    """y = D_matrix(D, d, k, n) * x with the matrix assembled slab by slab as the reference's column loop does
+    and applied by CSC column scatter (full-size stand-in for the 7.5 GB assembled matrix); returns (y, nnz)."""
+    hc, hr, hv = _H_arrays(H)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    nnz = lib().gsgo_apply_D_assembled(D, k, n, _SCHEME[scheme], d, _p(hc), _p(hr), _p(hv), _p(x), _p(y), slab_cols)
+    if nnz < 0:
+        raise RuntimeError("gsgo_apply_D_assembled failed")
+    return y, int(nnz)
+
+
+def rk4_advect(D, k, n, H, a, u0, dt, nsteps, scheme="sparse"):
+    """Classical RK4 (gsg_oracle.rk4 stage order) of u' = -sum_d a_d D_d u with the C pole apply."""
+    def rhs(u):
+        acc = np.zeros_like(u)
+        for d in range(1, D + 1):
+            if a[d - 1] != 0.0:
+                acc += a[d - 1] * apply_D_poles(D, d, k, n, H, u, scheme)
+        return -acc
+    y = np.array(u0, dtype=np.float64)
+    for _ in range(nsteps):
+        k1 = rhs(y)
+        k2 = rhs(y + (0.5 * dt) * k1)
+        k3 = rhs(y + (0.5 * dt) * k2)
+        k4 = rhs(y + dt * k3)
+        y = y + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+    return y
 
 
 def total_nnz(D, k, n, H, scheme="sparse"):

@@ -163,6 +163,107 @@ void gsgo_spmv_csc(int64_t ncols, const int64_t* colptr, const int64_t* rowval, 
     }
 }
 
+/* y = D_d x through the per-pole principal-sub-block identity (verified against the
+ * assembled matrix in tests): every pole (1-D fibre along axis d) is multiplied by H[0:N', 0:N'],
+ * N' = k 2^(n - s).  Inside a pole the product runs column by column, y[row] += val * x[col], i.e. every
+ * output row is accumulated in ascending global column order, multiply-then-add: the same per-row
+ * summation order as Julia's CSC column scatter on the assembled D_d (src/pdes.jl:63 `RHS*x`).
+ * Poles are independent (they write disjoint rows), so items run in parallel (OpenMP). */
+int gsgo_apply_D_poles(int D, int k, int n, int scheme, int d, const int64_t* Hcolptr, const int64_t* Hrowval,
+                       const double* Hnzval, const double* x, double* y) {
+    if (D > MAXD) return -1;
+    index_set* Sp = cached_index_set(D, k, n, scheme);
+    if (!Sp) return -1;
+    const index_set S = *Sp;
+    const int dd = d - 1;
+    int64_t radix[MAXD];
+    radix[0] = 1;
+    for (int i = 1; i < D; ++i) radix[i] = radix[i - 1] * (n + 1);
+    const int64_t mstride_d = ipow(k, dd);
+    const int64_t nmode_other = S.kD / k;
+    int rc = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b0 = 0; b0 < S.nblocks; ++b0) {
+        const int* lv = S.level + (int64_t)b0 * D;
+        if (lv[dd] != 0) continue;
+        int sum_other = 0;
+        int64_t tkey = 0;
+        for (int i = 0; i < D; ++i) if (i != dd) { sum_other += lv[i]; tkey += radix[i] * lv[i]; }
+        const int p = scheme == 1 ? n : n - sum_other;
+        const int64_t Np = (int64_t)k << p;
+        int C[MAXD];
+        int64_t stride_lo = 1, stride_hi = 1;
+        for (int i = 0; i < D; ++i) C[i] = cells_of(lv[i]);
+        for (int i = 0; i < dd; ++i) stride_lo *= C[i];
+        for (int i = dd + 1; i < D; ++i) stride_hi *= C[i];
+        int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * Np);
+        double* xp = (double*)malloc(sizeof(double) * Np);
+        double* yp = (double*)malloc(sizeof(double) * Np);
+        if (!idx || !xp || !yp) { rc = -1; free(idx); free(xp); free(yp); continue; }
+        for (int64_t hi = 0; hi < stride_hi; ++hi)
+            for (int64_t lo = 0; lo < stride_lo; ++lo) {
+                /* base index of every 1-D entry (l2, c2, m2) of the pole with other modes = 0 */
+                for (int64_t i1 = 0; i1 < Np; ++i1) {
+                    const int q = (int)(i1 / k), m2 = (int)(i1 % k);
+                    int l2 = 0, c2 = 0;
+                    if (q > 0) { l2 = 1; while ((1 << l2) <= q) ++l2; c2 = q - (1 << (l2 - 1)); }
+                    const int b2 = S.table[tkey + radix[dd] * l2];
+                    const int64_t C2 = cells_of(l2);
+                    idx[i1] = S.offset[b2] + (lo + stride_lo * (c2 + C2 * hi)) * S.kD + m2 * mstride_d;
+                }
+                for (int64_t mo = 0; mo < nmode_other; ++mo) {
+                    /* other-mode offset: digits of mo spread around axis d */
+                    const int64_t mofs = (mo % mstride_d) + (mo / mstride_d) * mstride_d * k;
+                    for (int64_t i1 = 0; i1 < Np; ++i1) { xp[i1] = x[idx[i1] + mofs]; yp[i1] = 0.0; }
+                    for (int64_t j1 = 0; j1 < Np; ++j1) {
+                        const double xj = xp[j1];
+                        for (int64_t pp = Hcolptr[j1]; pp < Hcolptr[j1 + 1]; ++pp) {
+                            const int64_t i1 = Hrowval[pp];
+                            if (i1 >= Np) break;                 /* rows sorted: outside the principal sub-block */
+                            yp[i1] += Hnzval[pp] * xj;
+                        }
+                    }
+                    for (int64_t i1 = 0; i1 < Np; ++i1) y[idx[i1] + mofs] = yp[i1];
+                }
+            }
+        free(idx); free(xp); free(yp);
+    }
+    return rc;
+}
+
+/* y += D_d x with D_d ASSEMBLED column slab by column slab exactly as the reference assembles it
+ * (gsgo_assemble_cols = the column loop of src/multidim_derivative.jl:32-55) and applied by CSC column
+ * scatter (gsgo_spmv_csc): the full-size stand-in for `D_matrix(D, d, k, n) * x` without holding the
+ * 7.5 GB matrix.  y must be zeroed by the caller.  Returns the total nnz, or -1. */
+int64_t gsgo_apply_D_assembled(int D, int k, int n, int scheme, int d, const int64_t* Hcolptr,
+                               const int64_t* Hrowval, const double* Hnzval, const double* x, double* y,
+                               int64_t slab_cols) {
+    index_set* Sp = cached_index_set(D, k, n, scheme);
+    if (!Sp) return -1;
+    const int64_t N = Sp->N;
+    int64_t maxcol = 0;
+    {   /* widest column of H bounds the slab's nnz */
+        const int64_t N1 = (int64_t)k << n;
+        for (int64_t j = 0; j < N1; ++j) if (Hcolptr[j + 1] - Hcolptr[j] > maxcol) maxcol = Hcolptr[j + 1] - Hcolptr[j];
+    }
+    const int64_t cap = slab_cols * maxcol;
+    int64_t* colptr = (int64_t*)malloc(sizeof(int64_t) * (slab_cols + 1));
+    int64_t* rowval = (int64_t*)malloc(sizeof(int64_t) * cap);
+    double* nzval = (double*)malloc(sizeof(double) * cap);
+    if (!colptr || !rowval || !nzval) { free(colptr); free(rowval); free(nzval); return -1; }
+    int64_t total = 0;
+    for (int64_t b = 0; b < N; b += slab_cols) {
+        const int64_t e = b + slab_cols < N ? b + slab_cols : N;
+        const int64_t nnz = gsgo_assemble_cols(D, k, n, scheme, d, Hcolptr, Hrowval, Hnzval, b, e, colptr, rowval,
+                                               nzval, cap);
+        if (nnz < 0 || nnz > cap) { total = -1; break; }
+        gsgo_spmv_csc(e - b, colptr, rowval, nzval, x + b, y);
+        total += nnz;
+    }
+    free(colptr); free(rowval); free(nzval);
+    return total;
+}
+
 /* row-parallel CSR product (MKLSparse analogue): y[i] = sum_p val[p] * x[col[p]] */
 void gsgo_spmv_csr_omp(int64_t nrows, const int64_t* rowptr, const int64_t* col, const double* val,
                        const double* x, double* y) {
@@ -177,6 +278,15 @@ void gsgo_spmv_csr_omp(int64_t nrows, const int64_t* rowptr, const int64_t* col,
 /* y += a * x on n entries (the allocating vector arithmetic of the integrator, serial) */
 void gsgo_axpy(int64_t n, double a, const double* x, double* y) {
     for (int64_t i = 0; i < n; ++i) y[i] += a * x[i];
+}
+
+void gsgo_set_threads(int nthreads) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
 }
 
 int gsgo_max_threads(void) {

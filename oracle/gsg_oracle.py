@@ -843,6 +843,65 @@ def reconstruct_DG(D: int, k: int, n: int, vect, xs, scheme: str = "sparse") -> 
     return value
 
 
+def _array2poly_vec(vv, x):
+    """array2poly (src/1d_dg_functions.jl:15-28) on an array of x: same operation order as `array2poly`
+    above (Horner, multiply-then-add, flipsign on the sign BIT, 0 outside [-1, 1])."""
+    x = np.asarray(x, dtype=np.float64)
+    half = len(vv) // 2
+    neg = np.signbit(x)
+    s = np.zeros_like(x)
+    for i in range(half - 1, -1, -1):
+        t = np.where(neg, -vv[i + half], vv[i + half])
+        s = s * x + (vv[i] + t)
+    return np.where(np.abs(x) > 1.0, 0.0, s)
+
+
+def reconstruct_DG_batch(D: int, k: int, n: int, vect, pts, scheme: str = "sparse"):
+    """reconstruct_DG (src/dg_methods.jl:150-165) for an (npts, D) array of points, vectorised over the
+    points with numpy; per point the SAME operation order as `reconstruct_DG` above (multi-levels in layout
+    order, modes first dim fastest, product accumulated from 1.0 over i = 1..D, value += coeff * product).
+    Validated against the scalar restatement in tests/test_oracle_pins.py."""
+    blocks, N = block_table(D, k, n, scheme)
+    vect = np.asarray(vect, dtype=np.float64)
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, D)
+    npts = pts.shape[0]
+    kD = k ** D
+    leg = leg_coeffs()
+    dg = dg_coeffs(k)
+    sqrt2 = math.sqrt(2.0)
+    # 1-D tables: cell (1-based) and basis values for every (dim, level, mode)
+    cell = np.empty((D, n + 1, npts), dtype=np.int64)
+    val = np.empty((D, n + 1, k, npts))
+    for i in range(D):
+        x = pts[:, i]
+        for l in range(n + 1):
+            if l <= 1:
+                c = np.ones(npts, dtype=np.int64)
+            else:
+                c = np.where(x >= 1.0, 1 << (l - 1), 1 + np.floor((1 << (l - 1)) * x).astype(np.int64))
+            cell[i, l] = c
+            for m in range(1, k + 1):
+                if l == 0:                      # v: LegendreP(m-1, 2x-1)*sqrt(2)   (src/dg_methods.jl:27-36)
+                    val[i, l, m - 1] = _array2poly_vec(leg[m - 1], 2.0 * x - 1.0) * sqrt2
+                else:                           # h(k, m, 2^l x - (2c-1)) * 2^(l/2)
+                    val[i, l, m - 1] = _array2poly_vec(dg[m - 1], (1 << l) * x - (2 * c - 1)) * math.sqrt(1.0 * (1 << l))
+    value = np.zeros(npts)
+    modes = list(cartesian_indices((k,) * D))
+    for lv, off, ks in blocks:
+        lin = np.zeros(npts, dtype=np.int64)
+        stride = 1
+        for i in range(D):
+            lin += (cell[i, lv[i]] - 1) * stride
+            stride *= ks[i]
+        base = off + lin * kD
+        for e, mode in enumerate(modes):
+            ans = np.ones(npts)
+            for i in range(D):
+                ans = ans * val[i, lv[i], mode[i] - 1]
+            value += vect[base + e] * ans
+    return value
+
+
 # ----------------------------------------------------------------------------
 # L4: drivers (fixed-step classical RK4; ODE.jl's adaptive ode45/ode78 are
 # third-party and not under /root/reference -- see SURVEY.md 8c)
@@ -883,6 +942,26 @@ def wave_rhs(mats):
         for A in mats:
             lu += A @ (A @ u)
         return np.concatenate([vv, lu])
+    return rhs
+
+
+def laplacian_matrix_ref(mats):
+    """laplacian_matrix (src/multidim_derivative.jl:71-79) in the REFERENCE's form: the explicit sparse
+    products `lap += D_op * D_op`, then `lap * x`.  `mats` are scipy CSC D_d (mid sizes); the literal
+    Gustavson product `spmatmul` of this module is used by the small-size pin."""
+    lap = None
+    for A in mats:
+        P = (A @ A).tocsc()
+        lap = P if lap is None else (lap + P).tocsc()
+    lap.sort_indices()
+    return lap
+
+
+def wave_rhs_ref(L):
+    """[u; v]' = [v; L u] with the assembled L (src/pdes.jl:22-49: RHS = [[0 I];[L 0]])."""
+    def rhs(y):
+        N = y.size // 2
+        return np.concatenate([y[N:], L @ y[:N]])
     return rhs
 
 

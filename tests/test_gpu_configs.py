@@ -1,0 +1,311 @@
+"""GPU parity at the sizes BASELINE.json names (task 1): the CUDA path through the C ABI
+against the CPU oracle at config 2 (D=2,k=3,n=8), config 3 (D=4,k=3,n=7), config 4 (D=6,k=3,n=8, full vector
+against the assembled CSC SpMV of oracle/csc_kernels.c) and config 5 (D=4,k=4,n=8 reconstruct), the Laplacian in
+the reference's `(D*D)*x` form, a 256-step run, and the streaming kernel for every compiled K.
+Tolerance: 1e-12 relative in Float64 (BASELINE.json north_star), ||y - y_ref||_2 / ||y_ref||_2."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import f_cos, f_gauss, f_sin, product_state, random_state, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _scipy(H):
+    import scipy.sparse as sp
+    return sp.csc_matrix((H.nzval, H.rowval, H.colptr), shape=(H.m, H.n))
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cbaseline
+    return cbaseline
+
+
+@pytest.fixture(scope="module")
+def plans(gsg, oracle):
+    cache = {}
+
+    def get(D, k, n, scheme="sparse"):
+        key = (D, k, n, scheme)
+        if key not in cache:
+            H = oracle.periodic_DLF_matrix(k, n)
+            cache[key] = (gsg.Plan(D, k, n, scheme, H=_scipy(H)), H)   # the SAME 1-D matrix on both sides
+        return cache[key]
+
+    return get
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 2: 2-D traveling wave, sparse k=3 n=8 (N = 11,520)
+# ---------------------------------------------------------------------------------------------------------
+def _traveling_wave_state(oracle, k, n, m=(1, 2)):
+    """u0 = cos(2 pi m.x), v0 = omega sin(2 pi m.x) from 1-D sin/cos vectors via tensor_construct, as
+    examples/traveling_wave.jl:18-48 does (cos(a+b) = cos a cos b - sin a sin b)."""
+    D = len(m)
+    assert D == 2
+    c = [oracle.coeffs_1d(k, n, lambda x, mi=mi: math.cos(2 * math.pi * mi * x)) for mi in m]
+    s = [oracle.coeffs_1d(k, n, lambda x, mi=mi: math.sin(2 * math.pi * mi * x)) for mi in m]
+    cc = oracle.tensor_construct(D, k, n, [c[0], c[1]])
+    ss = oracle.tensor_construct(D, k, n, [s[0], s[1]])
+    sc = oracle.tensor_construct(D, k, n, [s[0], c[1]])
+    cs = oracle.tensor_construct(D, k, n, [c[0], s[1]])
+    omega = 2 * math.pi * math.sqrt(sum(mi * mi for mi in m))
+    return cc - ss, omega * (sc + cs)
+
+
+def test_config2_apply_every_axis(plans, oracle, cb):
+    D, k, n = 2, 3, 8
+    plan, H = plans(D, k, n)
+    assert plan.size == 11520
+    u0, v0 = _traveling_wave_state(oracle, k, n)
+    for x in (u0, random_state(plan.size, seed=2)):
+        for d in (1, 2):
+            ref = oracle.apply_D_poles(D, d, k, n, x, H=H)
+            assert relerr(plan.apply_D(d, x), ref) <= TOL
+            # the oracle's pole identity against the reference-style assembled matrix at this size
+            A = cb.D_matrix(D, d, k, n, H)
+            assert relerr(A @ x, ref) <= 1e-14
+
+
+def test_config2_laplacian_reference_form(plans, oracle, cb):
+    """`laplacian_matrix(D,k,n) * x` with the Laplacian built as the reference builds it: explicit sparse
+    products D_d * D_d summed, then applied (src/multidim_derivative.jl:71-79)."""
+    D, k, n = 2, 3, 8
+    plan, H = plans(D, k, n)
+    mats = [cb.D_matrix(D, d, k, n, H) for d in (1, 2)]
+    L = oracle.laplacian_matrix_ref(mats)
+    u0, _ = _traveling_wave_state(oracle, k, n)
+    for x in (u0, random_state(plan.size, seed=3)):
+        ref = L @ x
+        err = relerr(plan.apply_laplacian(x), ref)
+        print(f"config 2 Laplacian vs (D*D)x: {err:.3e}")
+        assert err <= TOL
+
+
+def test_config2_wave_rk4_16_steps(plans, oracle, cb):
+    D, k, n = 2, 3, 8
+    plan, H = plans(D, k, n)
+    mats = [cb.D_matrix(D, d, k, n, H) for d in (1, 2)]
+    L = oracle.laplacian_matrix_ref(mats)
+    u0, v0 = _traveling_wave_state(oracle, k, n)
+    dt, nsteps = 1.0e-4, 16
+    ref = oracle.rk4(oracle.wave_rhs_ref(L), np.concatenate([u0, v0]), dt, nsteps)
+    u, v = plan.rk4_wave(u0, v0, dt, nsteps)
+    err = relerr(np.concatenate([u, v]), ref)
+    print(f"config 2 wave RK4 x16 vs reference-form oracle: {err:.3e}")
+    assert err <= TOL
+    assert relerr(u, u0) > 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 3: 4-D phase space, sparse k=3 n=7 (N = 327,888): the Ds[d]*f applies and a 16-step advection
+# ---------------------------------------------------------------------------------------------------------
+def _vlasov_state(oracle, k, n):
+    """f0 = 2 pi prod_x exp(-2 pi^2 (x-1/2)^2) prod_v exp(-2 pi^2 v^2)   (examples/vlasov_evolve.jl:20-27)"""
+    gx = oracle.coeffs_1d(k, n, lambda x: math.exp(-2 * math.pi ** 2 * (x - 0.5) ** 2))
+    gv = oracle.coeffs_1d(k, n, lambda x: math.exp(-2 * math.pi ** 2 * x ** 2))
+    return 2 * math.pi * oracle.tensor_construct(4, k, n, [gx, gx, gv, gv])
+
+
+def test_config3_apply_every_axis(plans, oracle, cb):
+    D, k, n = 4, 3, 7
+    plan, H = plans(D, k, n)
+    assert plan.size == 327888
+    f0 = _vlasov_state(oracle, k, n)
+    for x in (f0, random_state(plan.size, seed=4)):
+        for d in range(1, D + 1):
+            ref = cb.apply_D_poles(D, d, k, n, H, x)
+            assert relerr(plan.apply_D(d, x), ref) <= TOL
+    # C pole oracle == assembled CSC scatter (bit for bit) and == the numpy pole oracle
+    x = random_state(plan.size, seed=5)
+    ya, nnz = cb.apply_D_assembled(D, 2, k, n, H, x)
+    assert nnz > 5_000_000
+    assert np.array_equal(ya, cb.apply_D_poles(D, 2, k, n, H, x))
+    assert relerr(oracle.apply_D_poles(D, 2, k, n, x, H=H), ya) <= 1e-15
+
+
+def test_config3_advection_rk4_16_steps(plans, oracle, cb):
+    D, k, n = 4, 3, 7
+    plan, H = plans(D, k, n)
+    f0 = _vlasov_state(oracle, k, n)
+    a = np.array([1.0, -0.5, 0.25, 2.0])
+    dt, nsteps = 1.0e-4, 16
+    ref = cb.rk4_advect(D, k, n, H, a, f0, dt, nsteps)
+    for mode in (0, 1):                       # Taylor form and staged form
+        plan.set_rk4_mode(mode)
+        try:
+            out = plan.rk4_advect(a, f0, dt, nsteps)
+        finally:
+            plan.set_rk4_mode(0)
+        err = relerr(out, ref)
+        print(f"config 3 advection RK4 x16 mode {mode}: {err:.3e}")
+        assert err <= TOL
+    assert relerr(out, f0) > 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 4: 6-D advection, sparse k=3 n=8 (N = 34,455,456) -- full vectors
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.timeout(1800)
+def test_config4_full_vector_vs_assembled_csc_and_rk4(gsg, oracle, cb):
+    D, k, n = 6, 3, 8
+    H = oracle.periodic_DLF_matrix(k, n)
+    plan = gsg.Plan(D, k, n, "sparse", H=_scipy(H))
+    assert plan.size == 34455456
+    v_sin = oracle.coeffs_1d(k, n, f_sin)
+    v_gau = oracle.coeffs_1d(k, n, f_gauss)
+    u_sin = gsg.tensor_construct(D, k, n, [v_sin] * D)
+    u_gau = gsg.tensor_construct(D, k, n, [v_gau] * D)
+    x = u_sin + 0.5 * u_gau + 1e-3 * np.random.default_rng(11).standard_normal(plan.size)
+    # (i) one D_d apply, d = 1 and d = 6, against D_matrix(D,d,k,n) * x assembled by the reference's column loop
+    for d in (1, 6):
+        ref, nnz = cb.apply_D_assembled(D, d, k, n, H, x)
+        assert nnz > 400_000_000
+        out = plan.apply_D(d, x)
+        err = relerr(out, ref)
+        print(f"config 4 full-vector D_{d} x vs assembled CSC ({nnz} nnz): {err:.3e}")
+        assert err <= TOL
+        assert np.array_equal(ref, cb.apply_D_poles(D, d, k, n, H, x))      # pins the C pole oracle at full size
+    # every other direction against the C pole oracle
+    for d in (2, 3, 4, 5):
+        assert relerr(plan.apply_D(d, x), cb.apply_D_poles(D, d, k, n, H, x)) <= TOL
+    # (ii) gradient combination
+    coef = np.array([1.0, -0.5, 0.25, 2.0, -1.5, 0.75])
+    gref = sum(coef[d - 1] * cb.apply_D_poles(D, d, k, n, H, x) for d in range(1, D + 1))
+    assert relerr(plan.apply_grad(coef, x), gref) <= TOL
+    # (iv) RK4 state after 16 steps, sin-product data, against the C-oracle RK4
+    a = np.ones(D)
+    dt, nsteps = 1.0e-4, 16
+    ref = cb.rk4_advect(D, k, n, H, a, u_sin, dt, nsteps)
+    out = plan.rk4_advect(a, u_sin, dt, nsteps)
+    err = relerr(out, ref)
+    print(f"config 4 RK4 x16 (sin-product) vs C-oracle RK4: {err:.3e}")
+    assert err <= TOL
+    assert relerr(out, u_sin) > 1e-4
+    # Gaussian data, 4 steps, staged driver
+    ref = cb.rk4_advect(D, k, n, H, a, u_gau, dt, 4)
+    plan.set_rk4_mode(1)
+    out = plan.rk4_advect(a, u_gau, dt, 4)
+    plan.set_rk4_mode(0)
+    err = relerr(out, ref)
+    print(f"config 4 RK4 x4 (Gaussian, staged) vs C-oracle RK4: {err:.3e}")
+    assert err <= TOL
+    plan.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 5: reconstruct_DG of a D=4 sparse k=4 n=8 interpolant on the default_rng(20240) prefix
+# ---------------------------------------------------------------------------------------------------------
+def test_config5_reconstruct_prefix(plans, oracle):
+    D, k, n = 4, 4, 8
+    plan, _ = plans(D, k, n)
+    assert plan.size == 2686976
+    vect = oracle.tensor_construct(D, k, n, [oracle.coeffs_1d(k, n, f_sin)] * D)
+    pts = np.random.default_rng(20240).random((1_000_000, D))
+    npar = 4096
+    ref = oracle.reconstruct_DG_batch(D, k, n, vect, pts[:npar])
+    out = plan.reconstruct(vect, pts)
+    assert out.shape == (1_000_000,)
+    err = np.abs(out[:npar] - ref).max() / np.abs(ref).max()
+    print(f"config 5 reconstruct, first {npar} of the 1e6 prefix vs oracle: {err:.3e}")
+    assert err <= TOL
+    # the whole prefix against the exact function (interpolation error of the k=4, n=8 sparse space)
+    exact = np.prod(np.sin(2 * np.pi * pts), axis=1)
+    assert np.sqrt(np.mean((out - exact) ** 2)) < 1e-6
+    # boundary points and cell edges
+    edge = np.array([[0.0] * D, [1.0] * D, [0.5] * D, [0.25, 0.5, 0.75, 1.0], [1.0 / 3, 0.125, 0.0, 0.999999]])
+    assert np.abs(plan.reconstruct(vect, edge) - oracle.reconstruct_DG_batch(D, k, n, vect, edge)).max() <= TOL
+
+
+def test_reconstruct_out_of_domain_points_raise(gsg, plans, oracle):
+    """The reference raises BoundsError for points outside [0, 1] (coeffs[key][cell], src/dg_methods.jl:158-159)."""
+    plan, _ = plans(2, 3, 4)
+    vect = product_state(oracle, 2, 3, 4, f_cos)
+    for bad in ([-0.1, 0.5], [0.5, 1.5], [float("nan"), 0.5]):
+        with pytest.raises(gsg.GsgError):
+            plan.reconstruct(vect, np.array([bad]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 256 steps at a mid size, Laplacian forms, every K of the streaming kernel
+# ---------------------------------------------------------------------------------------------------------
+def test_rk4_256_steps_mid_size(plans, oracle, cb):
+    D, k, n = 3, 3, 6
+    plan, H = plans(D, k, n)
+    u0 = product_state(oracle, D, k, n, f_sin) + 0.25 * product_state(oracle, D, k, n, f_gauss)
+    a = np.array([1.0, 0.5, -0.75])
+    dt, nsteps = 2.0e-4, 256
+    ref = cb.rk4_advect(D, k, n, H, a, u0, dt, nsteps)
+    out = plan.rk4_advect(a, u0, dt, nsteps)
+    err = relerr(out, ref)
+    print(f"RK4 x256 at (3,3,6): {err:.3e}")
+    assert err <= TOL
+    assert relerr(out, u0) > 1e-2
+
+
+@pytest.mark.parametrize("D,k,n,scheme", [(2, 3, 6, "sparse"), (3, 3, 5, "sparse"), (2, 4, 5, "sparse"), (2, 2, 4, "full")])
+def test_laplacian_reference_form(plans, oracle, D, k, n, scheme):
+    plan, H = plans(D, k, n, scheme)
+    mats = [oracle.D_matrix_poles(D, d, k, n, scheme=scheme, H=H) for d in range(1, D + 1)]
+    L = oracle.laplacian_matrix_ref(mats)
+    x = product_state(oracle, D, k, n, f_sin, scheme=scheme) + 0.1 * random_state(plan.size, seed=9)
+    err = relerr(plan.apply_laplacian(x), L @ x)
+    print(f"Laplacian ({D},{k},{n},{scheme}) vs (D*D)x: {err:.3e}")
+    assert err <= TOL
+
+
+def test_laplacian_literal_gustavson_small(plans, oracle):
+    """Smallest case with the oracle's literal Gustavson sparse product (Julia's `D_op * D_op`)."""
+    D, k, n = 2, 3, 3
+    plan, H = plans(D, k, n)
+    x = random_state(plan.size, seed=13)
+    ref = np.zeros(plan.size)
+    for d in (1, 2):
+        A = oracle.D_matrix_literal(D, d, k, n, H=H)
+        ref += oracle.spmatmul(A, A).matvec(x)
+    assert relerr(plan.apply_laplacian(x), ref) <= TOL
+
+
+@pytest.mark.parametrize("D,k,n", [(9, 2, 2), (5, 4, 2), (4, 5, 2), (6, 3, 3)])
+def test_streaming_kernel_every_K(plans, oracle, cb, D, k, n):
+    """(D, k) with k^D >= 365 route the short poles through sweep_stream_kernel<K, false> (and PAIR tiles through
+    <K, true>): K = 2, 4, 5 besides the K = 3 of the headline config."""
+    plan, H = plans(D, k, n)
+    x = random_state(plan.size, seed=D + k)
+    for d in (1, D // 2 + 1, D):
+        assert relerr(plan.apply_D(d, x), cb.apply_D_poles(D, d, k, n, H, x)) <= TOL
+    a = np.linspace(0.5, 1.5, D)
+    ref = sum(a[d - 1] * cb.apply_D_poles(D, d, k, n, H, x) for d in range(1, D + 1))
+    assert relerr(plan.apply_grad(a, x), ref) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side API wrappers (reference names) through the GPU path
+# ---------------------------------------------------------------------------------------------------------
+def test_api_wrappers_wave_energy_mcerr(gsg, oracle):
+    """wave_evolve / energy_func / mcerr / reconstruct_DG(dict) as a user of the reference would call them
+    (test/solvers.jl:54-77: sqrt(E) ~ sqrt(2) pi, energy non-increasing to 1e-8; examples/interpolation.jl)."""
+    D, k, n = 2, 3, 5
+    f0 = gsg.tensor_construct(D, k, n, [gsg.vcoeffs_DG(1, k, n, f_sin)] * D)
+    v0 = np.zeros_like(f0)
+    soln = gsg.wave_evolve(D, k, n, f0, v0, 0.0, 0.25, order="4", nout=5)
+    times, energies = gsg.energy_func(D, k, n, soln)
+    assert times.shape == (5,) and energies.shape == (5,)
+    assert np.all(np.abs(np.sqrt(energies) - math.sqrt(2) * math.pi) < 1e-4)
+    assert abs(energies[0] - energies[-1]) < 1e-8
+    # advect_evolve: one period of u_t + u_x + u_y = 0 returns the initial data
+    u1 = gsg.advect_evolve(D, k, n, [1.0, 1.0], f0, 0.0, 1.0)
+    assert relerr(u1, f0) < 1e-4
+    # mcerr against the exact function, from a coefficient vector and from the dict
+    g = lambda p: math.sin(2 * math.pi * p[0]) * math.sin(2 * math.pi * p[1])
+    e_vec = gsg.mcerr(f0, g, D, k, n, count=1000, rng=np.random.default_rng(3))
+    e_dict = gsg.mcerr(gsg.V2D(D, k, n, f0), g, D, k, n, count=1000, rng=np.random.default_rng(3))
+    assert e_vec == e_dict and e_vec < 2.0 ** -(n + k - 2)           # test/hier_DG.jl:58 bound
+    d = gsg.V2D(D, k, n, f0)
+    one = gsg.reconstruct_DG(d, [0.3, 0.7])
+    assert abs(one - oracle.reconstruct_DG(D, k, n, f0, [0.3, 0.7])) <= 1e-12

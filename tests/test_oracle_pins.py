@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import f_cos, f_sin, product_state, relerr
+from helpers import f_cos, f_gauss, f_sin, product_state, relerr
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -166,6 +166,43 @@ def test_assembly_identities(oracle):
             assert np.array_equal(A.toarray(), Cm.toarray())
             # CSC column scatter == per-pole ascending-column accumulation, bit for bit
             assert np.array_equal(A.matvec(x), oracle.apply_D_poles(D, d, k, n, x, scheme=scheme, H=H))
+
+
+def test_c_pole_oracle_and_batch_reconstruct(oracle):
+    """The C pole apply / slab-assembled CSC apply (oracle/csc_kernels.c) == the literal assembly's column
+    scatter, bit for bit; the numpy-batched reconstruct == the scalar restatement, bit for bit."""
+    import cbaseline
+    for D, k, n, scheme in [(2, 3, 4, "sparse"), (3, 2, 3, "sparse"), (2, 2, 3, "full"), (4, 2, 2, "sparse")]:
+        H = oracle.periodic_DLF_matrix(k, n)
+        x = np.random.default_rng(1).standard_normal(oracle.get_size(D, k, n, scheme))
+        for d in range(1, D + 1):
+            lit = oracle.D_matrix_literal(D, d, k, n, scheme=scheme, H=H)
+            ref = lit.matvec(x)
+            assert np.array_equal(cbaseline.apply_D_poles(D, d, k, n, H, x, scheme=scheme), ref)
+            ya, nnz = cbaseline.apply_D_assembled(D, d, k, n, H, x, scheme=scheme, slab_cols=97)
+            assert nnz == lit.nnz and np.array_equal(ya, ref)
+    for D, k, n, scheme in [(1, 3, 5, "sparse"), (2, 3, 4, "sparse"), (2, 2, 3, "full"), (3, 4, 3, "sparse")]:
+        vect = product_state(oracle, D, k, n, f_sin, scheme=scheme) + 0.1 * product_state(oracle, D, k, n, f_gauss, scheme=scheme)
+        pts = np.random.default_rng(2).random((24, D))
+        pts[0], pts[1], pts[2], pts[3] = 0.0, 1.0, 0.5, 0.25
+        a = np.array([oracle.reconstruct_DG(D, k, n, vect, list(p), scheme=scheme) for p in pts])
+        assert np.array_equal(a, oracle.reconstruct_DG_batch(D, k, n, vect, pts, scheme=scheme))
+
+
+def test_laplacian_reference_form(oracle):
+    """laplacian_matrix = sum_d D_d*D_d as explicit sparse products (src/multidim_derivative.jl:71-79): the scipy
+    product used at mid sizes == the literal Gustavson product, and (D*D)x vs D(Dx) differ only by rounding."""
+    D, k, n = 2, 3, 3
+    H = oracle.periodic_DLF_matrix(k, n)
+    x = np.random.default_rng(4).standard_normal(oracle.get_size(D, k, n))
+    mats = [oracle.D_matrix_poles(D, d, k, n, H=H) for d in (1, 2)]
+    L = oracle.laplacian_matrix_ref(mats)
+    lit = np.zeros_like(x)
+    for d in (1, 2):
+        A = oracle.D_matrix_literal(D, d, k, n, H=H)
+        lit += oracle.spmatmul(A, A).matvec(x)
+    assert relerr(L @ x, lit) < 1e-14
+    assert relerr(sum(A @ (A @ x) for A in mats), lit) < 1e-13
 
 
 def test_tensor_construct_matches_projection(oracle):

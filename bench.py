@@ -244,23 +244,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    mg = drv = None
     if world == 1:
         def run(nsteps):
             plan.rk4_advect_dev(a, y, DT, nsteps)
-    else:
+    elif os.environ.get("GSG_MG_NCCL"):
+        # portable path: the same block partition driven from Python with NCCL point-to-point messages
         from gsg_b200.distributed import DistComm, PartitionedRK4
         drv = PartitionedRK4(plan, a, rank, world, device, DistComm())
         drv.set_state(y)
 
         def run(nsteps):
             drv.step(DT, nsteps)
+    else:
+        # shipped path: the partitioned RK4 runs inside libgsgb200 over peer-mapped slabs (CUDA IPC); torch.distributed
+        # only carries the 64-byte handles once and the barriers around the timed region
+        from gsg_b200.distributed import MultiGpuRK4
+        del y
+        torch.cuda.empty_cache()
+        mg = MultiGpuRK4(plan, rank, world)
+        mg.connect_torch()
+        dist.barrier()
+        mg.set_state(u0)
+        mg.sync()
+        dist.barrier()
+
+        def run(nsteps):
+            mg.step(a, DT, nsteps)
 
     run(W)
     barrier()
     sampler = ClockSampler(local_rank)
     # CUDA events around the dominant kernel for a bounded sample of the timed region's launches (the first
     # 72 = two steps' worth: timing all of them costs ~8 % of the step, this sample ~0.5 %)
-    plan.profile_enable(0 if os.environ.get("GSG_NO_PROFILE_EVENTS") else 72)
+    # (the in-library multi-GPU driver replays the step from a CUDA graph: its sample is taken after the timed region)
+    plan.profile_enable(0 if (os.environ.get("GSG_NO_PROFILE_EVENTS") or mg is not None) else 72)
     l0 = g.launch_count()
     sampler.start()
     barrier()
@@ -276,10 +294,16 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    if world > 1 and os.environ.get("GSG_PART_TIMING"):
+    if drv is not None and os.environ.get("GSG_PART_TIMING"):
         rep = drv.timing_report()
         print(f"[rank {rank}] owned {100.0 * drv.owned_doubles / plan.dev_size:.1f}% phases (device ms, host ms): "
               + "; ".join(f"{k_}: {v_[0]:.3f}/{v_[1]:.3f} mean {v_[2]:.3f} max {v_[3]:.3f}" for k_, v_ in rep.items()), file=sys.stderr, flush=True)
+    if mg is not None and not os.environ.get("GSG_NO_PROFILE_EVENTS"):
+        barrier()
+        plan.profile_enable(72)
+        mg.step(a, DT, 2)                       # eager (not replayed) steps with events around the dominant kernel
+        mg.sync()
+        barrier()
     n_prof, prof_ms, prof_dofs = plan.profile_read()
     plan.profile_enable(False)
     value = N * K / (ms * 1e-3)
@@ -315,7 +339,6 @@ def main():
         }
 
     # ---- e2e: the C-ABI evolve call on HOST buffers (H2D + K steps + D2H inside the timed region)
-    e2e = None
     if world == 1:
         host = torch.from_numpy(u0.copy()).pin_memory()
         hv = host.numpy()
@@ -331,8 +354,26 @@ def main():
                "d2h_bytes_per_step": 8.0 * N / K,
                "call": f"gsg_rk4_advect(plan, a, y_host(pinned), dt, nsteps={K}): one H2D + {K} RK4 steps + one D2H",
                "seconds": t1 - t0}
+    elif mg is not None:
+        # every rank: owned blocks of the pinned host state -> device, K steps, owned blocks -> pinned host
+        host = torch.from_numpy(u0.copy()).pin_memory()
+        out_host = torch.zeros(N, dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        mg.set_state(host.numpy())
+        mg.step(a, DT, K)
+        mg.get_state(out_host.numpy())          # synchronises this rank
+        barrier()
+        t1 = time.perf_counter()
+        tt = torch.tensor([t1 - t0], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt.item())
+        frac, xbytes = mg.owned_fraction()
+        e2e = {"value": N * K / sec, "unit": "DOF-updates/s", "h2d_bytes_per_step": 8.0 * N * frac / K,
+               "d2h_bytes_per_step": 8.0 * N * frac / K, "seconds": sec,
+               "call": f"per rank: gsg_mg_set_state(pinned host state; owned blocks H2D) + gsg_mg_rk4_advect(dt, {K}) + "
+                       "gsg_mg_get_state(owned blocks D2H); wall clock, max over ranks"}
     else:
-        # every rank: pinned host state (reference layout) -> device, K partitioned steps, owned part -> pinned host
         host = torch.from_numpy(u0.copy()).pin_memory()
         ref_dev = torch.empty(N, dtype=torch.float64, device=device)
         full_dev = torch.zeros(plan.dev_size, dtype=torch.float64, device=device)
@@ -386,9 +427,14 @@ def main():
                        "parallelism": ("single GPU" if world == 1 else
                                        f"multi-level blocks partitioned over {world} GPUs by level==0 of the last "
                                        f"{world.bit_length() - 1} dimension(s); per RHS 2 point-to-point messages per "
-                                       f"partition dimension per rank pair (NCCL), "
-                                       f"{drv.exchange_bytes_per_rhs / 1e6:.1f} MB exchanged per RHS on rank 0, "
-                                       f"rank 0 owns {100.0 * drv.owned_doubles / plan.dev_size:.1f}% of the state")},
+                                       f"partition dimension per rank pair, "
+                                       + (f"{drv.exchange_bytes_per_rhs / 1e6:.1f} MB exchanged per RHS on rank 0, "
+                                          f"rank 0 owns {100.0 * drv.owned_doubles / plan.dev_size:.1f}% of the state"
+                                          if mg is None else
+                                          f"in-library driver (gsg_mg_*): peer-mapped slabs over CUDA IPC, pull / pull-add "
+                                          f"kernels over NVLink, flag counters, step replayed from a CUDA graph; rank 0 pulls "
+                                          f"{mg.owned_fraction()[1] / 1e6:.1f} MB per RHS and owns "
+                                          f"{100.0 * mg.owned_fraction()[0]:.1f}% of the state"))},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -72,6 +72,17 @@ SIGNATURES = {
     "gsg_plan_partition_blocks": (i32, [vp, i32, i32, vp, vp, p_i64, C.POINTER(i32)]),
     "gsg_rk4_taylor_cells_dev": (i32, [vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64]),
     "gsg_plan_set_rk4_mode": (i32, [vp, i32]),
+    "gsg_mg_create": (i32, [vp, i32, i32, C.POINTER(vp)]),
+    "gsg_mg_destroy": (i32, [vp]),
+    "gsg_mg_ipc_handle": (i32, [vp, vp]),
+    "gsg_mg_connect_ipc": (i32, [vp, vp]),
+    "gsg_mg_connect_local": (i32, [C.POINTER(vp), i32]),
+    "gsg_mg_set_state": (i32, [vp, vp]),
+    "gsg_mg_get_state": (i32, [vp, vp]),
+    "gsg_mg_owned_fraction": (i32, [vp, p_f64, p_i64]),
+    "gsg_mg_rk4_advect": (i32, [vp, vp, f64, i64]),
+    "gsg_mg_rk4_advect_all": (i32, [C.POINTER(vp), i32, vp, f64, i64]),
+    "gsg_mg_sync": (i32, [vp]),
     "gsg_rk_stage_dev": (i32, [vp, i64, vp, vp, vp, vp, f64, f64, i32]),
     "gsg_rk_final_dev": (i32, [vp, i64, vp, vp, vp, f64]),
     "gsg_profile_enable": (i32, [vp, i32]),

@@ -4,6 +4,8 @@
 #include "host_setup.hpp"
 #include "kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -44,6 +46,14 @@ int fail(int code, const std::string& msg) {
         int rc__ = (expr);         \
         if (rc__ != 0) return rc__;\
     } while (0)
+
+// NVTX range (tracing): visible in Nsight Systems / ncu --nvtx, a no-op without a tool attached
+struct nvtx_range {
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+    nvtx_range(const nvtx_range&) = delete;
+    nvtx_range& operator=(const nvtx_range&) = delete;
+};
 
 template <class T>
 struct DevBuf {                       // move-only owner of a device allocation
@@ -297,6 +307,13 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         P.short_pmax = p;
     }
     P.htotal = (int)all.size();
+    // the kernels' parameter struct HDense<K> always has room for every class up to ShortDims<K>::pmax():
+    // with n < pmax the unused classes are zero-filled
+    {
+        size_t want = 0;
+        for (int p = 0; p <= SHORT_MAX_P && (K << p) <= SHORT_MAX_NP; ++p) want += (((size_t)(K << p) * (K << p)) + 1) & ~(size_t)1;
+        if (all.size() < want) all.resize(want, 0.0);
+    }
     P.dense_host = all;
     return 0;
 }
@@ -1090,6 +1107,10 @@ int elementwise_grid(const gsg_plan& pl, int64_t N) {
 // y = alpha * D_d x + beta * y   (d 0-based; device layout); x and y must not alias.  The launches
 // of one sweep write disjoint parts of y, so they are forked onto auxiliary streams and joined.
 int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y, bool reduced = false) {
+    static const char* const names[16] = {"sweep d=1", "sweep d=2", "sweep d=3", "sweep d=4", "sweep d=5", "sweep d=6",
+                                          "sweep d=7", "sweep d=8", "sweep d=9", "sweep d=10", "sweep d=11", "sweep d=12",
+                                          "sweep", "sweep", "sweep", "sweep"};
+    nvtx_range nvtx_r(names[d & 15]);
     const Direction& dir = reduced ? pl.dirs_red[d] : pl.dirs[d];
     const size_t nc = dir.classes.size();
     if (beta != 0.0 && beta != 1.0) {     // kernels implement beta in {0, 1}
@@ -1142,6 +1163,7 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
 // y = beta0 * y + sum_{d in mask} c_d D_d x with the streaming classes of each direction pair fused (PAIR tiles)
 // where both directions of the pair are in the mask; every c_d in the mask must be non-zero
 int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y, unsigned mask = ~0u, double beta0 = 0.0) {
+    nvtx_range nvtx_r("rhs: fused gradient");
     const int K = pl.S.k, D = pl.S.D;
     const int npairs = (int)pl.pairs.size();
     bool first = true;
@@ -1262,6 +1284,7 @@ int rk4_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nsteps, Rh
     double* w = pl.ww.p;
     const int grid = elementwise_grid(pl, len);
     return run_steps(pl, nsteps, [&]() -> int {
+        nvtx_range nvtx_r("rk4 step (staged)");
         GSG_TRY(rhs(y, k));                                                        // k1
         rk_stage_kernel<<<grid, 256, 0, pl.stream>>>(len, y, k, acc, w, 0.5 * dt, dt / 6.0, 1);
         GSG_TRY(rhs(w, k));                                                        // k2
@@ -1293,6 +1316,7 @@ int rk4_linear_loop(gsg_plan& pl, int64_t len, double* y, double dt, int64_t nst
     double* v4 = pl.wv4.p;
     const int grid = elementwise_grid(pl, len);
     return run_steps(pl, nsteps, [&]() -> int {
+        nvtx_range nvtx_r("rk4 step (Taylor form)");
         GSG_TRY(rhs(y, v1));
         GSG_TRY(rhs(v1, v2));
         GSG_TRY(rhs(v2, v3));
@@ -2054,3 +2078,5 @@ int gsg_spmv_csc(int64_t m, int64_t n, const int64_t* colptr, const int64_t* row
 }
 
 }  // extern "C"
+
+#include "multi_gpu.inl"

@@ -1,10 +1,102 @@
-"""Multi-GPU RK4 for u' = -sum_d a_d D_d u: one process per GPU, torch.distributed for the plumbing
-(SURVEY.md section 8e).  Block-partitioned scheme:
+"""Multi-GPU RK4 for u' = -sum_d a_d D_d u.
+
+Two drivers of the same block partition:
+  * `MultiGpuRK4` -- the shipped path.  The whole partitioned RK4 runs inside libgsgb200 (gsg_mg_*): peer-mapped
+    state slabs, pull / pull-add kernels over NVLink, flag counters for rank synchronisation, the step replayed
+    from a CUDA graph.  Python only exchanges the 64-byte CUDA IPC handles once (torch.distributed all_gather,
+    any backend) -- nothing per right-hand side.
+  * `PartitionedRK4` -- the portable path: the same partition driven from Python with NCCL / gloo point-to-point
+    messages (kept for CPU tests of the control flow and as a fallback where peer mapping is unavailable).
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
+
+from ._lib import check, lib
+
+
+class MultiGpuRK4:
+    """One rank of the in-library multi-GPU RK4 (include/gsg_b200.h, gsg_mg_*)."""
+
+    def __init__(self, plan, rank: int, world: int):
+        self.plan, self.rank, self.world = plan, rank, world
+        h = C.c_void_p()
+        check(lib.gsg_mg_create(plan._h, rank, world, C.byref(h)))
+        self._h = h
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib.gsg_mg_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def connect_ipc(self, handles) -> None:
+        """handles: the 64-byte handles of all ranks in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        check(lib.gsg_mg_connect_ipc(self._h, C.c_char_p(blob)))
+
+    def connect_torch(self, group=None) -> None:
+        """Exchange the IPC handles through torch.distributed (one all_gather of 64 bytes per rank)."""
+        if self.world == 1:
+            self.connect_ipc([self.ipc_handle()])
+            return
+        mine = torch.frombuffer(bytearray(self.ipc_handle()), dtype=torch.uint8).clone()
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        mine = mine.to(dev)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=group)
+        self.connect_ipc([bytes(t.cpu().numpy().tobytes()) for t in out])
+
+    @staticmethod
+    def connect_local(ranks) -> None:
+        """ranks: every MultiGpuRK4 of the partition, living in this process (rank order)."""
+        arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+        check(lib.gsg_mg_connect_local(arr, len(ranks)))
+
+    def set_state(self, u_host: np.ndarray) -> None:
+        u_host = np.ascontiguousarray(u_host, dtype=np.float64)
+        assert u_host.shape == (self.plan.size,)
+        check(lib.gsg_mg_set_state(self._h, u_host.ctypes.data_as(C.c_void_p)))
+
+    def get_state(self, out_host: np.ndarray) -> np.ndarray:
+        assert out_host.dtype == np.float64 and out_host.flags.c_contiguous and out_host.shape == (self.plan.size,)
+        check(lib.gsg_mg_get_state(self._h, out_host.ctypes.data_as(C.c_void_p)))
+        return out_host
+
+    def owned_fraction(self):
+        f, b = C.c_double(), C.c_int64()
+        check(lib.gsg_mg_owned_fraction(self._h, C.byref(f), C.byref(b)))
+        return f.value, b.value
+
+    def step(self, a, dt: float, nsteps: int) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        check(lib.gsg_mg_rk4_advect(self._h, a.ctypes.data_as(C.c_void_p), float(dt), int(nsteps)))
+
+    @staticmethod
+    def step_all(ranks, a, dt: float, nsteps: int) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+        check(lib.gsg_mg_rk4_advect_all(arr, len(ranks), a.ctypes.data_as(C.c_void_p), float(dt), int(nsteps)))
+
+    def sync(self) -> None:
+        check(lib.gsg_mg_sync(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.gsg_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 # nranks = 2^b.  Dimension D-j (j < b) splits the multi-level blocks into {level == 0} (rank bit j = 1)
 # and {level >= 1} (bit 0): every block has exactly one owner, the shares are balanced to ~10 % at

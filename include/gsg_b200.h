@@ -148,6 +148,36 @@ int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncell
                              const double* v2, const double* v3, const double* v4, double c1, double c2, double c3,
                              double c4);
 
+/* ---- multi-GPU RK4 inside the library: peer-mapped state slabs, no NCCL on the data path ---------------------
+ * One gsg_mg per rank (one process per GPU, or several ranks inside one process).  gsg_mg_create partitions the
+ * plan (gsg_plan_set_partition) and allocates the rank's slab of 5 full-length vectors (u, v1..v4) plus a flag
+ * area; the slabs are mapped into the partner ranks' address spaces -- between processes through CUDA IPC handles
+ * (gsg_mg_ipc_handle / gsg_mg_connect_ipc; the host exchanges the 64-byte handles any way it likes), inside one
+ * process directly (gsg_mg_connect_local).  Per right-hand side and partition dimension the sweeping rank pulls
+ * the level-0 cells of the stage input out of its partner's slab over NVLink and the owner pull-adds the
+ * contribution; ranks synchronise through counters in each other's flag area, and a whole RK4 step replays from
+ * one CUDA graph.  u' = -sum_d a_d D_d u (BASELINE config 4; src/pdes.jl:179-180 operator). */
+typedef struct gsg_mg gsg_mg;
+#define GSG_MG_HANDLE_BYTES 64
+int gsg_mg_create(gsg_plan* plan, int rank, int nranks, gsg_mg** out);
+int gsg_mg_destroy(gsg_mg* mg);
+int gsg_mg_ipc_handle(gsg_mg* mg, void* handle64);
+/* handles: nranks consecutive 64-byte handles in rank order */
+int gsg_mg_connect_ipc(gsg_mg* mg, const void* handles);
+int gsg_mg_connect_local(gsg_mg* const* all, int nranks);
+/* COLLECTIVE (every rank, after a host-level barrier): load this rank's owned blocks from a full reference-layout
+ * host vector / write them back into one (entries of other ranks' blocks are left untouched) */
+int gsg_mg_set_state(gsg_mg* mg, const double* u_host);
+int gsg_mg_get_state(gsg_mg* mg, double* u_host);
+/* fraction of the state this rank owns; bytes it pulls over NVLink per right-hand side */
+int gsg_mg_owned_fraction(gsg_mg* mg, double* frac_out, int64_t* exchange_bytes_per_rhs_out);
+/* COLLECTIVE: nsteps classical RK4 steps (Taylor form), asynchronous on the plan's stream */
+int gsg_mg_rk4_advect(gsg_mg* mg, const double* a, double dt, int64_t nsteps);
+/* one host thread drives all ranks of the partition (phases enqueued in lockstep) */
+int gsg_mg_rk4_advect_all(gsg_mg* const* all, int nranks, const double* a, double dt, int64_t nsteps);
+/* wait for this rank's streams; reports a flag-wait timeout (20 s) as GSG_ERR_CUDA */
+int gsg_mg_sync(gsg_mg* mg);
+
 /* w = u + cw*k ; acc = (first ? u : acc) + ca*k   on `len` entries (any sub-range) */
 int gsg_rk_stage_dev(gsg_plan* plan, int64_t len, const double* u, const double* k, double* acc,
                      double* w, double cw, double ca, int first);

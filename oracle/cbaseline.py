@@ -170,6 +170,59 @@ def total_nnz(D, k, n, H, scheme="sparse"):
     return total
 
 
+def time_direction(D, d, k, n, H, x, threads=1, slab=1 << 18, scheme="sparse", workers=None):
+    """Time ONE COMPLETE product D_d x of the reference's CPU path: the whole assembled D_d, slab by slab (the
+    slabs are assembled by a thread pool, untimed -- the reference assembles once, outside its time loop -- and
+    each slab's SpMV is timed).  threads == 1: Julia's serial CSC column scatter (stock SparseArrays, `A*x` of
+    src/pdes.jl:63); threads > 1: OpenMP row-parallel CSR on the same entries (the optional MKLSparse path,
+    src/GalerkinSparseGrids.jl:5-7).  Returns (seconds of SpMV, nnz, y)."""
+    from concurrent.futures import ThreadPoolExecutor
+    N = get_size(D, k, n, scheme)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(N)
+    y += 0.0                                        # touch the pages: no first-write faults inside the timed SpMV
+    if threads > 1:
+        import scipy.sparse as sp
+        hc, hr, hv = _H_arrays(H)
+        Hs = sp.csc_matrix((hv, hr, hc), shape=(k << n, k << n)).T.tocsc()
+        Hs.sort_indices()
+        lib().gsgo_set_threads(int(threads))
+    else:
+        Hs = H
+    get_size(D, k, n, scheme)
+    assemble_cols(D, d, k, n, Hs, 0, 1, scheme)                      # builds the C side's cached index set
+    bounds = [(b, min(N, b + slab)) for b in range(0, N, slab)]
+    workers = workers or max(1, min(16, (os.cpu_count() or 1)))
+    t_spmv, nnz = 0.0, 0
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        group = 2 * workers
+        for g0 in range(0, len(bounds), group):
+            part = bounds[g0:g0 + group]
+            slabs = list(pool.map(lambda be: assemble_cols(D, d, k, n, Hs, be[0], be[1], scheme), part))
+            for (b, e), (colptr, rowval, nzval) in zip(part, slabs):
+                if threads == 1:
+                    xs = x[b:e]
+                    t0 = time.perf_counter()
+                    spmv_csc(colptr, rowval, nzval, xs, y)
+                    t_spmv += time.perf_counter() - t0
+                else:
+                    ys = y[b:e]
+                    t0 = time.perf_counter()
+                    lib().gsgo_spmv_csr_omp(e - b, _p(colptr), _p(rowval), _p(nzval), _p(x), _p(ys))
+                    t_spmv += time.perf_counter() - t0
+                nnz += nzval.size
+    return t_spmv, nnz, y
+
+
+def time_axpy(N, threads=1):
+    x = np.ones(N)
+    y = np.zeros(N)
+    lib().gsgo_axpy(N, 0.5, _p(x), _p(y))          # first pass touches the pages
+    t0 = time.perf_counter()
+    lib().gsgo_axpy(N, 0.5, _p(x), _p(y))
+    return time.perf_counter() - t0
+
+
 def rk4_cpu_baseline(D, k, n, H, budget_s=15.0, threads=1, chunk=4096, scheme="sparse", seed=0):
     """Estimate RK4 DOF-updates/s of the reference's CPU path at (D, k, n).
 

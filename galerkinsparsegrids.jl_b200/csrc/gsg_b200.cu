@@ -98,7 +98,7 @@ constexpr size_t SMEM_OPTIN_MAX = 227 * 1024;
 constexpr int SHORT_TILE_DOUBLES = 4096;
 constexpr int TMA_STAGE_TARGET_DOUBLES = 5840;
 
-enum class Kind { SHORT_TMA, LONG, LONG2, LONGU, CONSTH, GENERIC };   // LONG: transient tag while a class is being placed
+enum class Kind { SHORT_TMA, LONG, LONG2, CONSTH, GENERIC };   // LONG: transient tag while a class is being placed
 
 struct SweepClass {          // one launch of a sweep
     int p = 0;               // pole length class (SHORT_TMA: the largest short class it holds)
@@ -111,7 +111,6 @@ struct SweepClass {          // one launch of a sweep
     int nbuf = 4;            // ... and record-ring depth (2 with 16 warps)
     std::vector<std::unique_ptr<DevBuf<int>>> passBlk, passRow;
     DevBuf<TileL2> l2tiles;
-    const std::vector<std::vector<unsigned char>>* uchunks = nullptr;   // LONGU: record chunks (LongURecs<K> images, owned by the plan)
     size_t smem = 0;
     DevBuf<TileDev> tiles;
     DevBuf<TileS> stiles;
@@ -157,8 +156,6 @@ struct gsg_plan {
     std::map<std::pair<int, int>, std::vector<std::unique_ptr<ColPass>>> lpass;   // key (p, npass)
     std::vector<int> h_rowptr, h_col;    // host copy of the block CSR
     std::vector<double> h_val;
-    // uniform-datapath long kernel: per (p, warps per CTA) the record chunks, each a LongURecs<K> image
-    std::map<std::pair<int, int>, std::vector<std::vector<unsigned char>>> uchunks;
     // constant-bank kernel: per p, the pattern blocks' values in pattern order (empty = not usable)
     std::vector<std::vector<double>> consth_vals;
 
@@ -366,73 +363,6 @@ int get_col_passes(gsg_plan& P, int p, int npass, const std::vector<std::unique_
     return 0;
 }
 
-// Record chunks of class p for the uniform-datapath long kernel (cached per plan): consecutive whole block-rows,
-// as many as fit one LongURecs<K>; inside a chunk the rows are dealt to W warps in contiguous ranges balanced by
-// record count (+1 per row for the row's prologue / epilogue).  Returns false if the class does not fit the scheme.
-template <int K>
-bool build_uchunks_k(gsg_plan& P, int p, int W, std::vector<std::vector<unsigned char>>& out) {
-    using Rec = LongURecs<K>;
-    const int nq = 1 << p;
-    if (nq > 256 || W > 16) return false;
-    std::vector<std::vector<int>> rows(nq);
-    for (int q = 0; q < nq; ++q) {
-        for (int b = P.h_rowptr[q]; b < P.h_rowptr[q + 1]; ++b)
-            if (P.h_col[b] < nq) rows[q].push_back(b);
-        if ((int)rows[q].size() > Rec::NR) return false;
-    }
-    int q = 0;
-    while (q < nq) {
-        std::vector<unsigned char> img(sizeof(Rec), 0);
-        Rec* R = reinterpret_cast<Rec*>(img.data());
-        int nrec = 0, nrow = 0;
-        while (q < nq && nrow < Rec::NROW && nrec + (int)rows[q].size() <= Rec::NR) {
-            R->row_q[nrow] = (unsigned char)q;
-            R->row_rec[nrow] = (unsigned short)nrec;
-            for (int b : rows[q]) {
-                std::memcpy(R->h[nrec], P.h_val.data() + (size_t)b * P.KK2, sizeof(double) * K * K);
-                R->col[nrec] = (unsigned char)P.h_col[b];
-                ++nrec;
-            }
-            ++nrow;
-            ++q;
-        }
-        R->row_rec[nrow] = (unsigned short)nrec;
-        R->nrows = nrow;
-        // warp partition: cost of row r = records + 1
-        const long long total = nrec + nrow;
-        int r = 0;
-        R->warp_row[0] = 0;
-        for (int w = 1; w <= 16; ++w) {
-            if (w >= W) { R->warp_row[w] = (unsigned short)nrow; continue; }
-            const long long target = total * w / W;
-            while (r < nrow && (long long)R->row_rec[r] + r < target) ++r;
-            R->warp_row[w] = (unsigned short)std::max<int>(r, R->warp_row[w - 1]);
-        }
-        out.push_back(std::move(img));
-    }
-    return true;
-}
-
-const std::vector<std::vector<unsigned char>>* get_uchunks(gsg_plan& P, int p, int W) {
-    auto key = std::make_pair(p, W);
-    auto it = P.uchunks.find(key);
-    if (it == P.uchunks.end()) {
-        std::vector<std::vector<unsigned char>> ch;
-        bool ok = false;
-        switch (P.S.k) {
-            case 1: ok = build_uchunks_k<1>(P, p, W, ch); break;
-            case 2: ok = build_uchunks_k<2>(P, p, W, ch); break;
-            case 3: ok = build_uchunks_k<3>(P, p, W, ch); break;
-            case 4: ok = build_uchunks_k<4>(P, p, W, ch); break;
-            case 5: ok = build_uchunks_k<5>(P, p, W, ch); break;
-            default: break;
-        }
-        if (!ok) ch.clear();
-        it = P.uchunks.emplace(key, std::move(ch)).first;
-    }
-    return it->second.empty() ? nullptr : &it->second;
-}
-
 int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_np /* -1: keep every group */) {
     const gsg::IndexSet& S = P.S;
     const int D = S.D, K = S.k, n = S.n;
@@ -586,67 +516,6 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         // register-tiled / constant-bank kernels for the long classes of k <= 5; everything else (k > 5, short
         // classes whose stage does not fit shared memory) goes to the generic block-CSR kernel
         c.kind = (K <= 5 && !short_supported(K, p)) ? Kind::LONG : Kind::GENERIC;
-        // uniform-datapath kernel (matrix streamed as kernel-parameter record chunks): classes up to GSG_LONGU_PMAX
-        // (default 6: beyond that a class needs too many chunk launches; they stay on the register-tiled kernel)
-        static const int longu_pmin = getenv("GSG_LONGU_PMIN") ? atoi(getenv("GSG_LONGU_PMIN")) : 0;
-        static const int longu_pmax = getenv("GSG_LONGU_PMAX") ? atoi(getenv("GSG_LONGU_PMAX")) : 6;
-        if (c.kind == Kind::LONG && !getenv("GSG_NO_LONGU") && p >= longu_pmin && p <= longu_pmax && NQ <= 256) {
-            long long maxpoles = 0;
-            for (size_t gi = 0; gi < groups.size(); ++gi)
-                if (groups[gi].p == p) maxpoles = std::max(maxpoles, (long long)groups[gi].nitems * PI);
-            if (maxpoles == 0) continue;
-            int C = maxpoles > 32 ? 2 : 1;
-            if (const char* e = getenv("GSG_LONGU_C")) C = atoi(e) >= 2 ? 2 : 1;
-            // two staging buffers of {x tile, cell table} per CTA (the next tile loads while this one computes)
-            size_t xtile = 2 * ((size_t)NP * 32 * C * 8 + (size_t)NQ * sizeof(CellOfs));
-            if (xtile > 200 * 1024 && C == 2) { C = 1; xtile = 2 * ((size_t)NP * 32 * C * 8 + (size_t)NQ * sizeof(CellOfs)); }
-            if (xtile <= 200 * 1024) {
-                const int per_sm = (int)std::max<size_t>(1, (220 * 1024) / (xtile + 1024));
-                int W = std::max(2, std::min(16, (16 + per_sm - 1) / per_sm));
-                if (const char* e = getenv("GSG_LONGU_W")) W = std::max(1, std::min(16, atoi(e)));
-                const std::vector<std::vector<unsigned char>>* chunks = get_uchunks(P, p, W);
-                if (chunks) {
-                    std::vector<TileL2> tl2;
-                    const int PT = 32 * C;
-                    for (size_t gi = 0; gi < groups.size(); ++gi) {
-                        if (groups[gi].p != p) continue;
-                        const GroupDev& g = groups[gi];
-                        const long long np = (long long)g.nitems * PI;
-                        if (np > 0x7fffffffLL) return fail(GSG_ERR_UNSUPPORTED, "too many poles in a pole group");
-                        const int ctab = (int)celltab.size();
-                        for (int q = 0; q < NQ; ++q) {
-                            const int ld = q == 0 ? 0 : 32 - __builtin_clz((unsigned)q);
-                            const int cd = q == 0 ? 0 : q - (1 << (ld - 1));
-                            const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
-                            const long long KS = (long long)KDp * g.S;
-                            celltab.push_back(CellOfs{g.base[ld] + KS * cd, KS * Cd});
-                        }
-                        for (long long p0 = 0; p0 < np; p0 += PT) {
-                            TileL2 t;
-                            t.ctab = ctab;
-                            t.S = g.S;
-                            t.item0 = (int)(p0 / PI);
-                            t.j0 = (int)(p0 % PI);
-                            t.lo0 = t.item0 % g.S;
-                            t.hi0 = t.item0 / g.S;
-                            t.npoles = (int)std::min<long long>(PT, np - p0);
-                            t.part = 0;
-                            tl2.push_back(t);
-                        }
-                    }
-                    c.kind = Kind::LONGU;
-                    c.cpl = C;
-                    c.nwarps = W;
-                    c.smem = xtile;
-                    c.uchunks = chunks;
-                    c.ntiles = (int)tl2.size();
-                    c.rsplit = per_sm;              // CTAs per SM (persistent grid = min(tiles, SMs * per_sm))
-                    GSG_TRY(c.l2tiles.upload(tl2));
-                    dir.classes.push_back(std::move(c));
-                    continue;
-                }
-            }
-        }
         if (c.kind == Kind::LONG && K == 3 && (p == 4 || p == 5) && !P.consth_vals[p].empty()) {
             // constant-bank kernel: one warp per 32 consecutive (flattened) poles of one group
             std::vector<TileL2> tl2;
@@ -1161,37 +1030,6 @@ int launch_long2_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Sw
     return fail(GSG_ERR_UNSUPPORTED, "internal: register-tiled long kernel not instantiated");
 }
 
-template <int K, int C>
-int launch_longu_kc(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
-                    double* y, double alpha, double beta) {
-    auto kern = sweep_longu_kernel<K, C>;
-    static thread_local size_t configured = 0;
-    GSG_TRY(ensure_smem(kern, c.smem, configured));
-    if (c.ntiles == 0) return 0;
-    static_assert(sizeof(LongURecs<K>) + 256 < 32764, "record chunk must fit the kernel parameter space");
-    const int PI = (int)pl.S.kD / K;
-    static const int gmul = getenv("GSG_LONGU_GRID") ? atoi(getenv("GSG_LONGU_GRID")) : 0;
-    const int grid = std::min(c.ntiles, pl.sm_count * (gmul > 0 ? gmul : c.rsplit));      // persistent: CTAs loop over tiles
-    for (const std::vector<unsigned char>& img : *c.uchunks) {      // chunks cover disjoint block-rows
-        LongURecs<K> R;
-        std::memcpy(&R, img.data(), sizeof(R));
-        kern<<<grid, c.nwarps * 32, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.offtab.p,
-                                                  c.l2tiles.p, c.ntiles, c.p, (int)pl.S.kDp, dir.A, PI, R);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-    return launch_check("sweep_longu", K, c);
-}
-
-template <int K>
-int launch_longu_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
-                   double* y, double alpha, double beta) {
-    if constexpr (K >= 1 && K <= 5) {
-        if (c.cpl == 2) return launch_longu_kc<K, 2>(pl, st, dir, c, x, y, alpha, beta);
-        return launch_longu_kc<K, 1>(pl, st, dir, c, x, y, alpha, beta);
-    }
-    return fail(GSG_ERR_UNSUPPORTED, "internal: uniform-datapath long kernel not instantiated");
-}
-
 template <int K, int PP>
 int launch_consth_kp(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
                      double* y, double alpha, double beta) {
@@ -1251,10 +1089,8 @@ int launch_class(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swee
                  double* y, double alpha, double beta) {
     const int K = pl.S.k;
     switch (c.kind) {
-        case Kind::LONG: break;
         case Kind::SHORT_TMA: GSG_K_SWITCH(launch_short_tma, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::LONG2: GSG_K_SWITCH(launch_long2_k, pl, st, dir, c, x, y, alpha, beta); break;
-        case Kind::LONGU: GSG_K_SWITCH(launch_longu_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::CONSTH: return launch_consth(pl, st, dir, c, x, y, alpha, beta);
         case Kind::GENERIC:
             GSG_K_SWITCH(launch_generic_k, pl, st, dir, c, x, y, alpha, beta);

@@ -1105,151 +1105,6 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
 }
 
 // ------------------------------------------------------------------------------------------
-// Long poles, matrix streamed through the UNIFORM datapath (round 2; the shipped path for 32 < N' <= K * 64).
-// The register-tiled kernel above is bound by shared-memory delivery of H: every K x K block record is
-// broadcast-loaded into vector registers by all 32 lanes (18 wavefronts per record at K = 3).  Here a chunk of
-// block records travels as a __grid_constant__ kernel parameter (<= 32 KB) and is read with WARP-UNIFORM DYNAMIC
-// indices: ptxas turns `R.h[i][e]` into LDCU.64 UR, c[0x0][UR + imm] and feeds the uniform register straight into
-// DFMA R, R, UR, R -- the matrix costs no shared-memory bandwidth and no vector registers, whatever C is
-// (tools/micro/ldcu_stream.cu: 25-27 TFLOP/s fp64 at 16 warps per SM against 7-10 for the kernels above).
-// Uniformity is made provable by routing the warp index through REDUX (__reduce_max_sync -> uniform register).
-// One launch = one class p and one CHUNK of consecutive whole block-rows (all the records that fit the parameter
-// space); a CTA = one pole tile of 32*C poles (x tile xs[row][32*C] in shared memory, as above) whose W warps take
-// contiguous row ranges of the chunk (host-balanced by record count).  Global I/O as in sweep_long2_kernel.
-// ------------------------------------------------------------------------------------------
-template <int K>
-struct LongURecs {
-    static constexpr int KK = K * K;
-    static constexpr int NROW = 96;                                               // rows per chunk
-    static constexpr int NR = (32400 - 4 - 34 - NROW - 2 * (NROW + 1)) / (KK * 8 + 1);   // records per chunk
-    double h[NR][KK];                     // K x K blocks, row-major (m_out, m_in)
-    unsigned short row_rec[NROW + 1];     // first record of each row of the chunk (+ end)
-    unsigned short warp_row[17];          // row range of warp w: [warp_row[w], warp_row[w + 1])
-    unsigned char col[NR];                // block column of each record (class p <= 8: < 256)
-    unsigned char row_q[NROW];            // block-row (1-D cell) of each row of the chunk
-    int nrows;
-};
-static_assert(sizeof(LongURecs<3>) <= 32400 && sizeof(LongURecs<5>) <= 32400, "record chunk must fit the kernel parameter space");
-
-template <int K, int C>
-__global__ void __launch_bounds__(512)
-sweep_longu_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
-                   const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
-                   const TileL2* __restrict__ tiles, int ntiles, int p, int KDp, int A, int PI,
-                   const __grid_constant__ LongURecs<K> R) {
-    constexpr int PT = 32 * C;
-    const int NQ = 1 << p;
-    extern __shared__ __align__(128) unsigned char smraw[];
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int warp = tid >> 5, nwarp = nth >> 5;
-    const int lane = tid & 31;
-    // two buffers of {x tile xs[K * NQ][PT], the tile's cell table}: the next tile is staged while this one is computed
-    const unsigned xbytes = (unsigned)(K * NQ) * PT * 8u;
-    const unsigned bufbytes = xbytes + (unsigned)NQ * (unsigned)sizeof(CellOfs);
-    const unsigned sm_s = (unsigned)__cvta_generic_to_shared(smraw);
-
-    struct PoleC { long long u[C], v[C]; bool ok[C]; };
-    auto pole_consts = [&](const TileL2& t, PoleC& pc) {       // (no integer divisions: the tile carries its first item / pole)
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int pl = c * 32 + lane;
-            pc.ok[c] = pl < t.npoles;
-            int jj = t.j0 + (pc.ok[c] ? pl : 0), lo = t.lo0, hi = t.hi0;
-            while (jj >= PI) {
-                jj -= PI;
-                if (++lo == t.S) { lo = 0; ++hi; }
-            }
-            pc.u[c] = (long long)KDp * lo + offtab[jj];
-            pc.v[c] = hi;
-        }
-    };
-    auto stage = [&](const TileL2& t, const PoleC& pc, int buf) {      // asynchronous copies, coalesced per (cell, mode, c)
-        const CellOfs* ctab = celltab + t.ctab;
-        const unsigned xb = sm_s + buf * bufbytes + lane * 8;
-        for (int qq = warp; qq < NQ; qq += nwarp) {
-            const CellOfs co = ctab[qq];
-            const unsigned dst = xb + qq * (K * PT * 8);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const double* src = X + co.bq + pc.u[c] + co.kc * pc.v[c];
-#pragma unroll
-                for (int mo = 0; mo < K; ++mo) cp_async8_zfill(dst + (mo * PT + c * 32) * 8, src + A * mo, pc.ok[c]);
-            }
-        }
-        const unsigned cb = sm_s + buf * bufbytes + xbytes;
-        for (int qq = tid; qq < NQ; qq += nth) cp_async16(cb + qq * 16, ctab + qq);
-    };
-
-    // every index of the record walk is warp-uniform (REDUX result -> uniform registers)
-    const int wu = __reduce_max_sync(0xffffffffu, warp);
-    const int r0 = R.warp_row[wu], r1 = R.warp_row[wu + 1];
-
-    int ti = blockIdx.x;
-    if (ti >= ntiles) return;
-    TileL2 tcur = tiles[ti];
-    PoleC pcur;
-    pole_consts(tcur, pcur);
-    stage(tcur, pcur, 0);
-    cp_async_commit();
-    for (int it = 0; ti < ntiles; ti += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int tn = ti + gridDim.x;
-        TileL2 tnext = tcur;
-        PoleC pnext = pcur;
-        if (tn < ntiles) {
-            tnext = tiles[tn];
-            pole_consts(tnext, pnext);
-            stage(tnext, pnext, buf ^ 1);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();            // this tile has landed (my copies) ...
-        __syncthreads();               // ... and everybody's
-        const unsigned xs_s = sm_s + buf * bufbytes + lane * 8;
-        const CellOfs* ctab_s = reinterpret_cast<const CellOfs*>(smraw + (size_t)buf * bufbytes + xbytes);
-        for (int r = r0; r < r1; ++r) {
-            const int q = R.row_q[r];
-            const int i0 = R.row_rec[r], i1 = R.row_rec[r + 1];
-            const CellOfs co = ctab_s[q];
-            long long rowofs[C];
-            double yold[K][C], acc[K][C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                rowofs[c] = co.bq + pcur.u[c] + co.kc * pcur.v[c];
-#pragma unroll
-                for (int mo = 0; mo < K; ++mo) {
-                    acc[mo][c] = 0.0;
-                    yold[mo][c] = (accumulate && pcur.ok[c]) ? Y[rowofs[c] + A * mo] : 0.0;      // in flight during the row
-                }
-            }
-#pragma unroll 2
-            for (int i = i0; i < i1; ++i) {
-                const unsigned xa = xs_s + (unsigned)R.col[i] * (unsigned)(K * PT * 8);
-                double x[K][C];
-#pragma unroll
-                for (int mi = 0; mi < K; ++mi)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) x[mi][c] = lds_f64(xa + (mi * PT + c * 32) * 8);
-#pragma unroll
-                for (int mi = 0; mi < K; ++mi)
-#pragma unroll
-                    for (int mo = 0; mo < K; ++mo)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) acc[mo][c] = fma(R.h[i][mo * K + mi], x[mi][c], acc[mo][c]);
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int mo = 0; mo < K; ++mo)
-                    if (pcur.ok[c]) Y[rowofs[c] + A * mo] = accumulate ? fma(alpha, acc[mo][c], yold[mo][c]) : alpha * acc[mo][c];
-        }
-        __syncthreads();               // this buffer is refilled by the next iteration's staging
-        tcur = tnext;
-        pcur = pnext;
-    }
-    cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------
 // Medium poles (N' = 48, 96 at k = 3), matrix in the constant bank.  The block pattern of the 1-D
 // operator is structural -- block (q, r) is stored iff the closed supports of the two hierarchical
 // cells intersect or touch periodically (checked against the host's H at

@@ -22,7 +22,8 @@ __all__ = [
     "GsgError", "Plan", "get_plan", "get_size", "cell_index", "basis_v", "basis_tables",
     "periodic_DLF_matrix", "coeffs_DG", "vcoeffs_DG", "tensor_construct", "V2D", "D2V", "V2Dref",
     "D2Vref", "D_matrix", "grad_matrix", "laplacian_matrix", "reconstruct_DG", "mcerr",
-    "wave_evolve", "advect_evolve", "energy_func", "spmv_csc", "CsrMatrix", "device_info",
+    "wave_evolve", "wave_evolve_1D", "advect_evolve", "energy_func", "energy_func_1D", "pos_vcoeffs_DG", "OdeIntegrator",
+    "ode_solve", "RHS_ADVECT", "RHS_WAVE", "RHS_CSR", "spmv_csc", "CsrMatrix", "device_info",
     "launch_count",
 ]
 
@@ -524,25 +525,171 @@ def _steps(time0: float, time1: float, dt: float):
     return nsteps, (time1 - time0) / nsteps
 
 
+RHS_ADVECT, RHS_WAVE, RHS_CSR = 0, 1, 2
+
+
+class OdeIntegrator:
+    """Device-resident adaptive Runge-Kutta stepper (gsg_ode_*): the drop-in for ODE.jl's ode45 (Dormand-Prince
+    5(4)) / ode78 (Fehlberg 7(8)) calls of src/pdes.jl:62-68, 113-119, 206-213."""
+
+    def __init__(self, plan: "Plan", rhs_kind: int, y0, t0: float, t1: float, order: str = "45", a=None, A=None,
+                 reltol: float = 0.0, abstol: float = 0.0):
+        if order not in ("45", "78"):
+            raise ValueError("ArgumentError(:order)")
+        self.plan, self.A = plan, A                      # keep the matrix alive
+        y0 = _f64(y0)
+        self.n = y0.size
+        a_arr = _f64(a) if a is not None else None
+        h = C.c_void_p()
+        check(lib.gsg_ode_create(plan._h, rhs_kind, _ptr(a_arr) if a_arr is not None else None,
+                                 A._h if A is not None else None, int(order), float(reltol), float(abstol), _ptr(y0),
+                                 float(t0), float(t1), C.byref(h)))
+        self._h = h
+        self.t, self.done = float(t0), False
+
+    def step(self):
+        """advance to the next accepted step; returns (t, dt, done)"""
+        t, dt, done = C.c_double(), C.c_double(), C.c_int()
+        check(lib.gsg_ode_step(self._h, C.byref(t), C.byref(dt), C.byref(done)))
+        self.t, self.done = t.value, bool(done.value)
+        return t.value, dt.value, self.done
+
+    def state(self) -> np.ndarray:
+        y = np.empty(self.n)
+        check(lib.gsg_ode_state(self._h, _ptr(y)))
+        return y
+
+    def interp(self, tquery: float) -> np.ndarray:
+        y = np.empty(self.n)
+        check(lib.gsg_ode_interp(self._h, float(tquery), _ptr(y)))
+        return y
+
+    def stats(self) -> dict:
+        a, r, f = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.gsg_ode_stats(self._h, C.byref(a), C.byref(r), C.byref(f)))
+        return {"accepted": a.value, "rejected": r.value, "rhs_evals": f.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.gsg_ode_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ode_solve(plan: "Plan", rhs_kind: int, y0, tspan, order: str = "45", points: str = "all", a=None, A=None,
+              reltol: float = 0.0, abstol: float = 0.0, stats: dict | None = None):
+    """`ode45(F, y0, tspan; points)` / `ode78(...)` of ODE.jl on the device: returns (tout, yout) as ODE.jl does --
+    points="all": every accepted step plus the requested times strictly inside a step (Hermite); points="specified":
+    the requested times only (src/pdes.jl:207-213 uses this with range(t0, t1, length=nout))."""
+    tspan = [float(t) for t in tspan]
+    ode = OdeIntegrator(plan, rhs_kind, y0, tspan[0], tspan[-1], order, a=a, A=A, reltol=reltol, abstol=abstol)
+    tdir = 1.0 if tspan[-1] > tspan[0] else -1.0
+    tout, yout = [tspan[0]], [_f64(y0).copy()]
+    if points == "specified":
+        tout = list(tspan)
+        yout = yout + [None] * (len(tspan) - 1)
+    it = 1
+    t_prev = tspan[0]
+    while not ode.done:
+        t, dt, done = ode.step()
+        if points == "specified":
+            while it < len(tspan) and (tdir * tspan[it] < tdir * t or done):
+                yout[it] = ode.state() if tspan[it] == t else ode.interp(tspan[it])
+                it += 1
+        else:
+            while it < len(tspan) and tdir * t_prev < tdir * tspan[it] < tdir * t:
+                yout.append(ode.interp(tspan[it]))
+                tout.append(tspan[it])
+                it += 1
+            yout.append(ode.state())
+            tout.append(t)
+        t_prev = t
+    if stats is not None:
+        stats.update(ode.stats())
+    ode.close()
+    return tout, yout
+
+
 def wave_evolve(D: int, k: int, n: int, f0coeffs, v0coeffs, time0: float, time1: float,
-                order: str = "4", scheme: str = "sparse", dt: float | None = None, nout: int = 2):
+                order: str = "45", scheme: str = "sparse", dt: float | None = None, nout: int = 2, **kwargs):
     """wave_evolve(D, k, n, f0coeffs, v0coeffs, t0, t1; order, scheme) -- src/pdes.jl:54-70.
-    The reference hands the RHS closure to ODE.jl's adaptive ode45/ode78 (third-party); this
-    drop-in adds the fixed-step order="4" branch that runs resident on the GPU.  Returns
-    (times, [state_i]) with state = [u; v] like ODE.jl's (tout, yout)."""
-    if order not in ("4",):
-        raise ValueError("ArgumentError(:order): the B200 path implements order=\"4\" (fixed-step RK4)")
+    order "45" / "78": ODE.jl's adaptive ode45 / ode78 on the device (the reference's branches, (tout, yout) with
+    every accepted step); order "4": the added fixed-step RK4 branch (resident, `nout` equally spaced outputs).
+    Returns (times, [state_i]) with state = [u; v] like ODE.jl's (tout, yout)."""
     plan = get_plan(D, k, n, scheme)
+    u, v = _f64(f0coeffs).copy(), _f64(v0coeffs).copy()
+    if order in ("45", "78"):
+        tout, yout = ode_solve(plan, RHS_WAVE, np.concatenate([u, v]), [time0, time1], order=order, **kwargs)
+        return np.array(tout), yout
+    if order != "4":
+        raise ValueError("ArgumentError(:order)")
     if dt is None:
         dt = 0.25 * 2.785 / (math.sqrt(D) * 8.081 * (1 << n))   # RK4 stability, rho(H) = 8.081 2^n
     times = np.linspace(time0, time1, nout)
-    u, v = _f64(f0coeffs).copy(), _f64(v0coeffs).copy()
     states = [np.concatenate([u, v])]
     for t0, t1 in zip(times[:-1], times[1:]):
         ns, h = _steps(t0, t1, dt)
         u, v = plan.rk4_wave(u, v, h, ns)
         states.append(np.concatenate([u, v]))
     return times, states
+
+
+def pos_vcoeffs_DG(k: int, max_level: int, f, npts: int = 20) -> np.ndarray:
+    """pos_vcoeffs_DG(k, level, f) -- src/1d_dg_functions.jl:103-117: coefficients in the position basis
+    (cell-wise scaled Legendre functions), one Gauss rule per cell instead of hquadrature."""
+    xs, ws = np.polynomial.legendre.leggauss(npts)
+    ncell = 1 << max_level
+    out = np.empty(k * ncell)
+    sc = 2.0 ** (max_level / 2)
+    leg, _ = basis_tables(k)
+    for c in range(ncell):
+        a, b = c / ncell, (c + 1) / ncell
+        half, mid = 0.5 * (b - a), 0.5 * (a + b)
+        x = mid + half * xs
+        fx = np.array([f(float(xi)) for xi in x])
+        for m in range(k):
+            # basis(level, cell, mode, x) = sqrt(2) P_{m}(2 (2^l x - c) - 1) 2^(l/2), P in monomial coefficients
+            xi = 2.0 * (ncell * x - c) - 1.0
+            pv = np.zeros_like(xi)
+            for co in leg[m, :11][::-1]:
+                pv = pv * xi + co
+            out[k * c + m] = half * float(np.dot(ws, fx * pv * math.sqrt(2.0) * sc))
+    return out
+
+
+def wave_evolve_1D(k: int, max_level: int, f0, v0, time0: float, time1: float, basis: str = "hier", order: str = "45",
+                   **kwargs):
+    """wave_evolve_1D -- src/pdes.jl:89-121 (BASELINE config 1): D_op = periodic_DLF_matrix(k, n; basis),
+    laplac = D_op * D_op as an explicit sparse product, RHS = [[0 I]; [laplac 0]] (wave_data), integrated with
+    ode45 / ode78; the RHS matrix lives on the device as a resident CSR matrix (GSG_RHS_CSR)."""
+    import scipy.sparse as sp
+    if basis == "pos":
+        f0c, v0c = pos_vcoeffs_DG(k, max_level, f0), pos_vcoeffs_DG(k, max_level, v0)
+    elif basis == "hier":
+        f0c, v0c = vcoeffs_DG(1, k, max_level, f0), vcoeffs_DG(1, k, max_level, v0)
+    else:
+        raise ValueError(f"ArgumentError(:basis) {basis!r}")       # "nodal"/"point" are broken in the reference too
+    D_op = periodic_DLF_matrix(k, max_level, basis=basis)
+    laplac = (D_op @ D_op).tocsc()
+    N = f0c.size
+    RHS = sp.bmat([[None, sp.identity(N, format="csc")], [laplac, None]], format="csc")
+    A = CsrMatrix(RHS)
+    plan = get_plan(1, k, max_level, "sparse")
+    tout, yout = ode_solve(plan, RHS_CSR, np.concatenate([f0c, v0c]), [time0, time1], order=order, A=A, **kwargs)
+    return np.array(tout), yout
+
+
+def energy_func_1D(k: int, level: int, soln, basis: str = "hier"):
+    """energy_func_1D -- src/pdes.jl:239-255: |D_op u|^2 + |udot|^2 per saved state (generic SpMV for D_op)."""
+    times, states = soln
+    D_op = CsrMatrix(periodic_DLF_matrix(k, level, basis=basis))
+    N = states[0].size // 2
+    return np.array(times), np.array([float(np.sum((D_op @ s[:N]) ** 2) + np.sum(s[N:] ** 2)) for s in states])
 
 
 def advect_evolve(D: int, k: int, n: int, a, u0coeffs, time0: float, time1: float,

@@ -2080,3 +2080,4 @@ int gsg_spmv_csc(int64_t m, int64_t n, const int64_t* colptr, const int64_t* row
 }  // extern "C"
 
 #include "multi_gpu.inl"
+#include "ode.inl"

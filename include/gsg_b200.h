@@ -148,6 +148,26 @@ int gsg_rk4_taylor_cells_dev(gsg_plan* plan, const int* cells_dev, int64_t ncell
                              const double* v2, const double* v3, const double* v4, double c1, double c2, double c3,
                              double c4);
 
+/* ---- adaptive integrators: drop-in for ODE.jl's ode45 / ode78 --------------------------------------------
+ * `ode45((t,x)->RHS*x, y0, [t0,t1])` / `ode78(...)`  src/pdes.jl:62-68, 113-119, 206-213 (ODE.jl 2.4.0: Dormand-
+ * Prince 5(4) `bt_dopri5`, Fehlberg 7(8) `bt_feh78`, `oderk_adapt` step control; defaults reltol 1e-5, abstol 1e-8,
+ * 2-norm of the scaled error, maxstep |t1-t0|/2.5).  The state, the stages and all vector arithmetic stay on the
+ * device; the host receives one (error, nan) pair per attempted step.  The integrator is a stepper: every call of
+ * gsg_ode_step advances to the next ACCEPTED step, so the host rebuilds ODE.jl's (tout, yout) with points=:all by
+ * reading the state after each call, or points=:specified with gsg_ode_interp (3rd-order Hermite, as ODE.jl). */
+typedef struct gsg_ode gsg_ode;
+#define GSG_RHS_ADVECT 0      /* y' = -sum_d a[d] D_d y          state length N   (the operator of src/pdes.jl:179-180) */
+#define GSG_RHS_WAVE 1        /* [u; v]' = [v; L u]              state length 2N  (wave_data, src/pdes.jl:22-49)        */
+#define GSG_RHS_CSR 2         /* y' = A y, A a resident gsg_csr  state length A.m (wave_evolve_1D's RHS, src/pdes.jl:109-114) */
+/* method: 45 or 78; reltol / abstol <= 0 select ODE.jl's defaults; `a` only for GSG_RHS_ADVECT, `A` only for GSG_RHS_CSR */
+int gsg_ode_create(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, int method, double reltol, double abstol,
+                   const double* y0_host, double t0, double t1, gsg_ode** out);
+int gsg_ode_destroy(gsg_ode* ode);
+int gsg_ode_step(gsg_ode* ode, double* t_out, double* dt_out, int* done_out);
+int gsg_ode_state(gsg_ode* ode, double* y_host);
+int gsg_ode_interp(gsg_ode* ode, double tquery, double* y_host);
+int gsg_ode_stats(gsg_ode* ode, int64_t* accepted, int64_t* rejected, int64_t* rhs_evals);
+
 /* ---- multi-GPU RK4 inside the library: peer-mapped state slabs, no NCCL on the data path ---------------------
  * One gsg_mg per rank (one process per GPU, or several ranks inside one process).  gsg_mg_create partitions the
  * plan (gsg_plan_set_partition) and allocates the rank's slab of 5 full-length vectors (u, v1..v4) plus a flag

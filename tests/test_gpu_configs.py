@@ -408,3 +408,90 @@ def test_mg_two_processes_cuda_ipc(tmp_path, oracle, cb):
     ref = cb.rk4_advect(D, k, n, H, np.array([1.0, -0.5, 0.25]), u0, dt, nsteps)
     out = sum(np.load(str(tmp_path / f"part{r}.npy")) for r in range(world))
     assert relerr(out, ref) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# adaptive integrators on the device (gsg_ode_*): ODE.jl's ode45 / ode78 call sites
+# ---------------------------------------------------------------------------------------------------------
+def _csr(M):
+    import scipy.sparse as sp
+    return sp.csc_matrix((M.nzval, M.rowval, M.colptr), shape=(M.m, M.n)).tocsr()
+
+
+@pytest.mark.parametrize("order", ["45", "78"])
+def test_ode_wave_2d_reference_assertions(gsg, oracle, order):
+    """`wave_evolve(2, 3, 5, f0, v0, 0, 1; order)` (test/solvers.jl:54-77): the device integrator takes the same
+    accepted / rejected steps as the restated ODE.jl on the oracle operator, the final state agrees to 1e-12, and
+    the reference's own assertions hold: energy drop in (0, 1e-8), sqrt(E) ~ sqrt(2) pi to 1e-4."""
+    import ode_oracle as oo
+    D, k, n = 2, 3, 5
+    mats = [oracle.D_matrix_poles(D, d, k, n).tocsr() for d in (1, 2)]
+    L = oracle.laplacian_matrix_ref(mats).tocsr()
+    u0 = product_state(oracle, D, k, n, f_sin)
+    N = u0.size
+    F = lambda t, y: np.concatenate([y[N:], L @ y[:N]])
+    st_o = {}
+    t_ref, y_ref = oo.oderk_adapt(F, np.concatenate([u0, np.zeros(N)]), [0.0, 1.0], oo.TABLEAUS[order], stats=st_o)
+    H = oracle.periodic_DLF_matrix(k, n)
+    plan = gsg.Plan(D, k, n, "sparse", H=_scipy(H))
+    st_g = {}
+    tout, yout = gsg.ode_solve(plan, gsg.RHS_WAVE, np.concatenate([u0, np.zeros(N)]), [0.0, 1.0], order=order, stats=st_g)
+    assert (st_g["accepted"], st_g["rejected"]) == (st_o["accepted"], st_o["rejected"])
+    assert len(tout) == len(t_ref) and np.abs(np.array(tout) - np.array(t_ref)).max() < 1e-12
+    err = relerr(yout[-1], y_ref[-1])
+    print(f"ode{order} 2-D wave: {st_g}, final state vs oracle {err:.3e}")
+    assert err <= TOL
+    times, E = gsg.energy_func(D, k, n, (tout, yout))
+    assert 0 < E[0] - E[-1] < 1.0e-8
+    assert np.all(np.abs(np.sqrt(E) - math.sqrt(2) * math.pi) < 1.0e-4)
+    plan.close()
+
+
+@pytest.mark.parametrize("basis,order", [("pos", "45"), ("hier", "45"), ("hier", "78")])
+def test_config1_wave_evolve_1D(gsg, oracle, basis, order):
+    """BASELINE config 1 / test/solvers.jl:19-47: wave_evolve_1D(k, level, f0, v0, 0, 1; basis, order) through the
+    library (RHS matrix resident as CSR, integrator on the device): sqrt(E) ~ 2 pi to 1e-7 at every output, and the
+    trajectory equals the restated ODE.jl on the oracle's matrices."""
+    import scipy.sparse as sp
+
+    import ode_oracle as oo
+    f0 = lambda x: math.sin(2 * math.pi * x)
+    v0 = lambda x: 2 * math.pi * math.cos(2 * math.pi * x)
+    for k, level in ((4, 4), (3, 5)):                       # the reference's test sizes and the README example's
+        soln = gsg.wave_evolve_1D(k, level, f0, v0, 0.0, 1.0, basis=basis, order=order)
+        times, E = gsg.energy_func_1D(k, level, soln, basis=basis)
+        assert times[-1] == 1.0 and len(times) > 10
+        if (k, level) == (4, 4):
+            assert np.all(np.abs(np.sqrt(E) - 2 * math.pi) < 1.0e-7)
+        # oracle trajectory with the library's own matrices handed over (same inputs on both sides)
+        D_op = gsg.periodic_DLF_matrix(k, level, basis=basis).tocsr()
+        Lm = (D_op @ D_op).tocsr()
+        y0 = soln[1][0]
+        N = y0.size // 2
+        F = lambda t, y: np.concatenate([y[N:], Lm @ y[:N]])
+        t_ref, y_ref = oo.oderk_adapt(F, y0, [0.0, 1.0], oo.TABLEAUS[order])
+        assert len(t_ref) == len(times)
+        assert relerr(soln[1][-1], y_ref[-1]) <= 1e-11
+
+
+def test_ode_advect_specified_points(gsg, oracle, cb):
+    """points=:specified (what vlasov_evolve asks for, src/pdes.jl:207-213): Hermite-interpolated outputs at
+    range(t0, t1, length=nout) against the restated ODE.jl with the C pole oracle as right-hand side."""
+    import ode_oracle as oo
+    D, k, n = 3, 3, 4
+    H = oracle.periodic_DLF_matrix(k, n)
+    plan = gsg.Plan(D, k, n, "sparse", H=_scipy(H))
+    u0 = product_state(oracle, D, k, n, f_gauss)
+    a = np.array([1.0, -0.5, 0.25])
+    F = lambda t, y: -sum(a[d - 1] * cb.apply_D_poles(D, d, k, n, H, y) for d in range(1, D + 1))
+    tspan = np.linspace(0.0, 0.05, 6)
+    for order in ("45", "78"):
+        t_ref, y_ref = oo.oderk_adapt(F, u0, tspan, oo.TABLEAUS[order], points="specified")
+        tout, yout = gsg.ode_solve(plan, gsg.RHS_ADVECT, u0, tspan, order=order, points="specified", a=a)
+        assert list(tout) == list(t_ref)
+        worst = max(relerr(y, yr) for y, yr in zip(yout, y_ref))
+        print(f"ode{order} advection, specified points: {worst:.3e}")
+        assert worst <= TOL
+    with pytest.raises(ValueError):
+        gsg.wave_evolve(D, k, n, u0, u0, 0.0, 1.0, order="23")
+    plan.close()

@@ -229,3 +229,83 @@ def test_golden_fixtures(oracle):
     pts = z["pts"]
     r = np.array([oracle.reconstruct_DG(3, 3, 4, u, list(p)) for p in pts])
     assert np.abs(r - z["recon_sin_334"]).max() < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ODE.jl restatement (oracle/ode_oracle.py): tableau order conditions + the reference's own solver assertions
+# ---------------------------------------------------------------------------------------------------------
+def test_ode_tableaus_order_conditions():
+    import ode_oracle as oo
+    for bt, (p_main, p_emb) in ((oo.DOPRI5, (5, 4)), (oo.FEH78, (7, 8))):
+        a, c = np.array(bt["a"]), np.array(bt["c"])
+        assert np.abs(a.sum(axis=1) - c).max() < 1e-14                      # row sums
+        assert np.allclose(np.triu(a), 0.0)                                  # explicit
+        for row, order in zip(bt["b"], (p_main, p_emb)):
+            b = np.array(row)
+            # quadrature conditions sum b c^(j-1) = 1/j and the first tree conditions up to order 4
+            for j in range(1, order + 1):
+                assert abs(b @ c ** (j - 1) - 1.0 / j) < 1e-14, (bt["name"], order, j)
+            assert abs(b @ (a @ c) - 1.0 / 6) < 1e-14
+            assert abs(b @ (a @ c ** 2) - 1.0 / 12) < 1e-14
+            assert abs(b @ (c * (a @ c)) - 1.0 / 8) < 1e-14
+            assert abs(b @ (a @ (a @ c)) - 1.0 / 24) < 1e-14
+    assert oo.is_fsal(oo.DOPRI5) and not oo.is_fsal(oo.FEH78)
+
+
+def test_ode_empirical_orders():
+    """one embedded step of size h on y' = -y + sin t: local error of the main solution ~ h^(p+1)"""
+    import ode_oracle as oo
+    F = lambda t, y: -y + np.sin(t)
+    def exact(t):           # y(0) = 1
+        return 1.5 * np.exp(-t) + 0.5 * (np.sin(t) - np.cos(t))
+    for bt, p in ((oo.DOPRI5, 5), (oo.FEH78, 7)):
+        errs = []
+        for h in (0.4, 0.2):
+            ks = [None] * len(bt["c"])
+            y0 = np.array([1.0])
+            ks[0] = F(0.0, y0)
+            yt, _ = oo.rk_embedded_step(ks, y0, F, 0.0, h, bt)
+            errs.append(abs(yt[0] - exact(h)))
+        slope = math.log2(errs[0] / errs[1])
+        assert p + 0.5 < slope < p + 1.8, (bt["name"], slope)
+
+
+def test_ode_reference_solver_assertions(oracle):
+    """test/solvers.jl:19-77 against the restated ode45 / ode78 + the oracle operators: sqrt(E) ~ 2 pi (1e-7) for the
+    1-D wave in the position and hierarchical bases, sqrt(E) ~ sqrt(2) pi (1e-4) and an energy drop in (0, 1e-8)
+    for the 2-D sparse k=3 n=5 wave, with both integrators."""
+    import scipy.sparse as sp
+
+    import ode_oracle as oo
+    k, level = 4, 4
+    f0 = lambda x: math.sin(2 * math.pi * x)
+    v0 = lambda x: 2 * math.pi * math.cos(2 * math.pi * x)
+
+    def csr(M):
+        return sp.csc_matrix((M.nzval, M.rowval, M.colptr), shape=(M.m, M.n)).tocsr()
+
+    for basis, order in (("pos", "45"), ("hier", "45"), ("hier", "78")):
+        D_op = csr(oracle.periodic_DLF_matrix(k, level, basis))
+        if basis == "pos":
+            fc, vc = np.array(oracle.pos_vcoeffs_DG(k, level, f0)), np.array(oracle.pos_vcoeffs_DG(k, level, v0))
+        else:
+            fc, vc = oracle.coeffs_1d(k, level, f0), oracle.coeffs_1d(k, level, v0)
+        L = (D_op @ D_op).tocsr()                                   # laplac = *(D_op, D_op), src/pdes.jl:110
+        N = fc.size
+        F = lambda t, y: np.concatenate([y[N:], L @ y[:N]])         # RHS = [[0 I];[L 0]], src/pdes.jl:22-49
+        tout, yout = oo.oderk_adapt(F, np.concatenate([fc, vc]), [0.0, 1.0], oo.TABLEAUS[order])
+        assert tout[-1] == 1.0 and len(tout) > 10
+        for y in yout:                                              # energy_func_1D, src/pdes.jl:239-255
+            E = np.sum((D_op @ y[:N]) ** 2) + np.sum(y[N:] ** 2)
+            assert abs(math.sqrt(E) - 2 * math.pi) < 1.0e-7, (basis, order, math.sqrt(E) - 2 * math.pi)
+    D, k2, n2 = 2, 3, 5
+    mats = [oracle.D_matrix_poles(D, d, k2, n2).tocsr() for d in (1, 2)]
+    L = oracle.laplacian_matrix_ref(mats).tocsr()
+    u0 = product_state(oracle, D, k2, n2, f_sin)
+    N = u0.size
+    F = lambda t, y: np.concatenate([y[N:], L @ y[:N]])
+    for order in ("78", "45"):
+        tout, yout = oo.oderk_adapt(F, np.concatenate([u0, np.zeros(N)]), [0.0, 1.0], oo.TABLEAUS[order])
+        E = [sum(np.sum((A @ y[:N]) ** 2) for A in mats) + np.sum(y[N:] ** 2) for y in yout]
+        assert 0 < E[0] - E[-1] < 1.0e-8, (order, E[0] - E[-1])
+        assert all(abs(math.sqrt(e) - math.sqrt(2) * math.pi) < 1.0e-4 for e in E)

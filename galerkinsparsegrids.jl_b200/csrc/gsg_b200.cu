@@ -180,7 +180,13 @@ struct gsg_plan {
     // workspaces (device layout)
     DevBuf<double> wx, wy, wk, wacc, ww, wtmp, wred;
     DevBuf<double> wpts, wout;
-    DevBuf<int> tile_counter;     // dynamic tile scheduler of the persistent TMA kernel
+    DevBuf<int> tile_counter;     // dynamic tile schedulers of the persistent kernels: one slot per launch, round robin
+    int ctr_next = 0;
+    // concurrent right-hand side (rhs_concurrent): pool of high-priority streams for the long-pole launches of ALL
+    // directions, forked after the first (beta = 0) pieces and joined at the end
+    std::vector<cudaStream_t> pool;
+    std::vector<cudaEvent_t> pool_ev;
+    cudaEvent_t ev_p1 = nullptr;
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
 
@@ -931,7 +937,8 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
         std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
-        GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p, 0, sizeof(int), st));
+        int* const counter = pl.tile_counter.p + (pl.ctr_next++ & 63);       // launches may overlap: one slot each
+        GSG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         if (c.stream2) {
@@ -939,11 +946,11 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
             static thread_local size_t configured2 = 0;
             GSG_TRY(ensure_smem(kern2, c.smem, configured2));
             kern2<<<grid, STREAM_THREADS, c.smem, st>>>(x, y, alpha, 0.0, beta != 0.0 ? 1 : 0, c.s2tiles.p + tb, tn, hd,
-                                                         c.sprm, pl.tile_counter.p, pl.dbg);
+                                                         c.sprm, counter, pl.dbg);
         } else
         kern<<<grid, 32 * (SHORT_TMA_COMPUTE_WARPS + 1), c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.groups.p,
                                                                          c.stiles.p + tb, tn, hd, c.sprm,
-                                                                         pl.tile_counter.p, pl.dbg);
+                                                                         counter, pl.dbg);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, st));
             ++pl.prof_used;
@@ -969,11 +976,12 @@ int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
         std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
-        GSG_CUDA(cudaMemsetAsync(pl.tile_counter.p + 1, 0, sizeof(int), st));
+        int* const counter = pl.tile_counter.p + (pl.ctr_next++ & 63);
+        GSG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, st));
         kern<<<grid, StreamCfg<true>::THREADS, c.smem, st>>>(x, y, alpha_a, alpha_b, beta != 0.0 ? 1 : 0, c.s2tiles.p, c.ntiles, hd,
-                                                    c.sprm, pl.tile_counter.p + 1, nullptr);
+                                                    c.sprm, counter, nullptr);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, st));
             ++pl.prof_used;
@@ -1216,11 +1224,132 @@ bool can_fuse(const gsg_plan& pl, const double* c, unsigned mask = ~0u) {
     return true;
 }
 
+// ---- concurrent right-hand side -----------------------------------------------------------------------------
+// y = beta0 * y + sum_{d in mask} c_d D_d x with every accumulate launch a reduction at the L2 (bulk reduce-add in
+// the streaming kernels, RED.ADD.F64 in the long-pole kernels), so that all pieces that ACCUMULATE commute and can
+// be in flight together.  Phase 1 (only when beta0 == 0): the pieces that cover every cell exactly once write with
+// beta = 0 -- the first pair's PAIR tiles + its first reduced sweep, or the first plain sweep.  Phase 2: everything
+// else with beta = 1; the long-pole launches of ALL remaining directions go to a pool of high-priority streams at
+// once (their 30-50 us CTA lifetimes overlap each other and the streaming kernels instead of adding up sweep by
+// sweep), the SM-filling persistent kernels (PAIR tiles, streaming classes) follow one another on the main stream.
+// `pre_wait[d]` (optional): an event the pieces of direction d must wait for (multi-GPU: the pulled level-0 cells).
+struct PoolCtx {
+    gsg_plan& pl;
+    unsigned used = 0;
+    int next = 0;
+    explicit PoolCtx(gsg_plan& p) : pl(p) {}
+    int take(cudaStream_t* out, cudaEvent_t after, cudaEvent_t after2 = nullptr) {
+        const int i = next++ & 15;
+        if (!((used >> i) & 1u) && after) GSG_CUDA(cudaStreamWaitEvent(pl.pool[i], after, 0));
+        if (after2) GSG_CUDA(cudaStreamWaitEvent(pl.pool[i], after2, 0));
+        used |= 1u << i;
+        *out = pl.pool[i];
+        return 0;
+    }
+    int join() {
+        for (int i = 0; i < 16; ++i)
+            if ((used >> i) & 1u) {
+                GSG_CUDA(cudaEventRecord(pl.pool_ev[i], pl.pool[i]));
+                GSG_CUDA(cudaStreamWaitEvent(pl.stream, pl.pool_ev[i], 0));
+            }
+        used = 0;
+        return 0;
+    }
+};
+
+// one sweep's launches with beta = 1: long-pole classes to the pool, the streaming class to `deferred`
+int sweep_scatter(gsg_plan& pl, PoolCtx& ctx, int d, double alpha, const double* x, double* y, bool reduced,
+                  cudaEvent_t after, cudaEvent_t after2, std::vector<std::pair<const Direction*, const SweepClass*>>& deferred) {
+    const Direction& dir = reduced ? pl.dirs_red[d] : pl.dirs[d];
+    for (const SweepClass& c : dir.classes) {
+        if (c.kind == Kind::SHORT_TMA) { deferred.emplace_back(&dir, &c); continue; }
+        cudaStream_t st;
+        GSG_TRY(ctx.take(&st, after, after2));
+        GSG_TRY(launch_class(pl, st, dir, c, x, y, alpha, 1.0));
+    }
+    return 0;
+}
+
+int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x, double* y, double beta0,
+                   const cudaEvent_t* pre_wait = nullptr) {
+    nvtx_range nvtx_r("rhs: concurrent");
+    const int K = pl.S.k, D = pl.S.D;
+    if (beta0 != 0.0 && beta0 != 1.0) return fail(GSG_ERR_ARG, "beta must be 0 or 1");
+    const int npairs = (pl.pair_np >= 0) ? (int)pl.pairs.size() : 0;
+    auto pair_fused = [&](int j) {
+        const int da = 2 * j, db = da + 1;
+        return j < npairs && ((mask >> da) & 1) && ((mask >> db) & 1) && c[da] != 0.0 && c[db] != 0.0 &&
+               !(pre_wait && (pre_wait[da] || pre_wait[db]));
+    };
+    auto do_pair = [&](int j, double beta) -> int {
+        if (pl.pairs[j].ntiles == 0) return 0;
+        const int da = 2 * j, db = da + 1;
+        switch (K) {
+            case 1: return launch_pair<1>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+            case 2: return launch_pair<2>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+            case 3: return launch_pair<3>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+            case 4: return launch_pair<4>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+            case 5: return launch_pair<5>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+        }
+        return fail(GSG_ERR_UNSUPPORTED, "internal: pair fusion for k > 5");
+    };
+    // ---- phase 1: initialise y (beta0 == 0)
+    int first_dir = -1;                       // direction whose (reduced) sweep ran in phase 1
+    int first_pair = -1;
+    if (beta0 == 0.0) {
+        for (int d = 0; d < D && first_dir < 0; ++d) {
+            if (!((mask >> d) & 1) || c[d] == 0.0 || (pre_wait && pre_wait[d])) continue;
+            const int j = d / 2;
+            if ((d & 1) == 0 && pair_fused(j)) {
+                first_pair = j;
+                GSG_TRY(do_pair(j, 0.0));
+                GSG_TRY(sweep(pl, d, c[d], x, 0.0, y, true));
+            } else if ((d & 1) == 1 && pair_fused(j)) {
+                continue;                      // (cannot happen: the even member comes first)
+            } else {
+                GSG_TRY(sweep(pl, d, c[d], x, 0.0, y, false));
+            }
+            first_dir = d;
+        }
+        if (first_dir < 0) {                   // nothing to initialise from: y = 0 on the plan's cells
+            int d0 = 0;
+            while (d0 < D && pre_wait && pre_wait[d0]) ++d0;
+            if (d0 == D) return fail(GSG_ERR_UNSUPPORTED, "internal: no local direction to initialise the right-hand side");
+            GSG_TRY(sweep(pl, d0, 0.0, x, 0.0, y, false));
+        }
+    }
+    // ---- phase 2: everything else accumulates; long-pole launches first (pool), then the SM-filling kernels
+    GSG_CUDA(cudaEventRecord(pl.ev_p1, pl.stream));
+    PoolCtx ctx(pl);
+    std::vector<std::pair<const Direction*, const SweepClass*>> deferred;
+    std::vector<int> deferred_dir;
+    std::vector<int> pairs_todo;
+    for (int d = 0; d < D; ++d) {
+        if (!((mask >> d) & 1) || c[d] == 0.0) continue;
+        const int j = d / 2;
+        const bool fused = pair_fused(j);
+        if (d == first_dir) continue;
+        if (fused && (d & 1) == 0 && j != first_pair) pairs_todo.push_back(j);
+        const size_t n0 = deferred.size();
+        GSG_TRY(sweep_scatter(pl, ctx, d, c[d], x, y, fused, pl.ev_p1, pre_wait ? pre_wait[d] : nullptr, deferred));
+        for (size_t i = n0; i < deferred.size(); ++i) deferred_dir.push_back(d);
+    }
+    for (int j : pairs_todo) GSG_TRY(do_pair(j, 1.0));
+    for (size_t i = 0; i < deferred.size(); ++i) {
+        const int d = deferred_dir[i];
+        if (pre_wait && pre_wait[d]) GSG_CUDA(cudaStreamWaitEvent(pl.stream, pre_wait[d], 0));
+        GSG_TRY(launch_class(pl, pl.stream, *deferred[i].first, *deferred[i].second, x, y, c[d], 1.0));
+    }
+    return ctx.join();
+}
+
 // k = -sum_d a_d D_d w
 int advect_rhs(gsg_plan& pl, const double* a, const double* w, double* k) {
     {
         double c[16];
         for (int d = 0; d < pl.S.D; ++d) c[d] = -a[d];
+        static const bool serial = getenv("GSG_RHS_SERIAL") != nullptr;
+        if (!serial) return rhs_concurrent(pl, c, ~0u, w, k, 0.0);
         if (can_fuse(pl, c)) return grad_fused(pl, c, w, k);
     }
     bool first = true;
@@ -1504,7 +1633,14 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
         GSG_CUDA(cudaStreamCreateWithPriority(&P->aux[i], cudaStreamNonBlocking, prio_hi));
         GSG_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
     }
-    GSG_TRY(P->tile_counter.resize(4));
+    GSG_TRY(P->tile_counter.resize(64));
+    P->pool.assign(16, nullptr);
+    P->pool_ev.assign(16, nullptr);
+    for (int i = 0; i < 16; ++i) {
+        GSG_CUDA(cudaStreamCreateWithPriority(&P->pool[i], cudaStreamNonBlocking, prio_hi));
+        GSG_CUDA(cudaEventCreateWithFlags(&P->pool_ev[i], cudaEventDisableTiming));
+    }
+    GSG_CUDA(cudaEventCreateWithFlags(&P->ev_p1, cudaEventDisableTiming));
     GSG_TRY(build_matrix(*P, H_n, H_colptr, H_rowval, H_nzval));
     P->dirs.resize(D);
     for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d, P->dirs[d], -1));
@@ -1535,6 +1671,9 @@ int gsg_plan_destroy(gsg_plan* plan) {
     cudaDeviceSynchronize();
     for (cudaStream_t st : plan->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : plan->ev_done) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : plan->pool) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : plan->pool_ev) if (ev) cudaEventDestroy(ev);
+    if (plan->ev_p1) cudaEventDestroy(plan->ev_p1);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_pair_fork) cudaEventDestroy(plan->ev_pair_fork);
     if (plan->ev_pair_done) cudaEventDestroy(plan->ev_pair_done);
@@ -1764,6 +1903,8 @@ int gsg_apply_D_dev(gsg_plan* plan, int d, double alpha, const double* x_dev, do
 int gsg_apply_grad_dev(gsg_plan* plan, const double* a, const double* x_dev, double* y_dev) {
     GSG_TRY(check_plan(plan));
     if (!a || !x_dev || !y_dev || x_dev == y_dev) return fail(GSG_ERR_ARG, "bad pointers");
+    static const bool serial = getenv("GSG_RHS_SERIAL") != nullptr;
+    if (!serial) return rhs_concurrent(*plan, a, ~0u, x_dev, y_dev, 0.0);
     if (can_fuse(*plan, a)) return grad_fused(*plan, a, x_dev, y_dev);
     for (int d = 0; d < plan->S.D; ++d) GSG_TRY(sweep(*plan, d, a[d], x_dev, d == 0 ? 0.0 : 1.0, y_dev));
     return 0;
@@ -1779,6 +1920,12 @@ int gsg_apply_dirs_dev(gsg_plan* plan, const double* c, unsigned dmask, double b
     const int D = plan->S.D;
     dmask &= (D >= 32 ? ~0u : ((1u << D) - 1u));
     if (dmask == 0) return 0;
+    static const bool serial = getenv("GSG_RHS_SERIAL") != nullptr;
+    if (!serial) {
+        bool any = false;
+        for (int d = 0; d < D; ++d) any = any || (((dmask >> d) & 1) && c[d] != 0.0);
+        if (any || beta == 1.0) return rhs_concurrent(*plan, c, dmask, x_dev, y_dev, beta);
+    }
     if (can_fuse(*plan, c, dmask)) return grad_fused(*plan, c, x_dev, y_dev, dmask, beta);
     bool first = true;
     for (int d = 0; d < D; ++d) {

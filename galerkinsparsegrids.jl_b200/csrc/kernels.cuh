@@ -834,10 +834,7 @@ sweep_generic_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
         if (beta == 0.0) {
             for (int tt = lane; tt < TL; tt += 32) dstg[tab_g[tt]] = alpha * srcs[tab_s[tt]];
         } else {
-            for (int tt = lane; tt < TL; tt += 32) {
-                const int g = tab_g[tt];
-                dstg[g] = fma(alpha, srcs[tab_s[tt]], beta * dstg[g]);
-            }
+            for (int tt = lane; tt < TL; tt += 32) atomicAdd(&dstg[tab_g[tt]], alpha * srcs[tab_s[tt]]);      // beta == 1
         }
     }
 }
@@ -1011,24 +1008,17 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
 
     // ---- stream this warp's block records, software-pipelined one record ahead (two register
     //      sets used alternately)
-    double acc[K][C], yold[K][C];
+    double acc[K][C];
 #pragma unroll
     for (int m = 0; m < K; ++m)
 #pragma unroll
-        for (int c = 0; c < C; ++c) { acc[m][c] = 0.0; yold[m][c] = 0.0; }
+        for (int c = 0; c < C; ++c) acc[m][c] = 0.0;
 
     long long rowofs[C];
-    auto row_begin = [&](int qr) {      // element offsets of block-row qr; prefetch its old y
+    auto row_begin = [&](int qr) {      // element offsets of block-row qr
         const CellOfs co = ctab[qr];
 #pragma unroll
         for (int c = 0; c < C; ++c) rowofs[c] = co.bq + u[c] + co.kc * v[c];
-        if (accumulate) {
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-#pragma unroll
-                for (int mo = 0; mo < K; ++mo)
-                    if (ok[c]) yold[mo][c] = Y[rowofs[c] + A * mo];
-        }
     };
     auto fetch = [&](int i, LongOperands<K, C>& o) {
         if ((i & (LONG_CH - 1)) == 0 || i == b0) {
@@ -1069,8 +1059,12 @@ sweep_long2_kernel(const double* __restrict__ X, double* __restrict__ Y, double 
         for (int cc = 0; cc < C; ++cc)
 #pragma unroll
             for (int mo = 0; mo < K; ++mo) {
-                if (ok[cc])
-                    Y[rowofs[cc] + A * mo] = accumulate ? fma(alpha, acc[mo][cc], yold[mo][cc]) : alpha * acc[mo][cc];
+                if (ok[cc]) {
+                    // y += ... as a reduction at the L2 (RED.ADD.F64): no read-modify-write through the SM, and sweeps of
+                    // different directions may accumulate into y concurrently
+                    if (accumulate) atomicAdd(&Y[rowofs[cc] + A * mo], alpha * acc[mo][cc]);
+                    else Y[rowofs[cc] + A * mo] = alpha * acc[mo][cc];
+                }
                 acc[mo][cc] = 0.0;
             }
         ++q;
@@ -1185,17 +1179,12 @@ struct ConstHCtx {
 
 template <int K, int P, int Q>
 __device__ __forceinline__ void consth_rows(const HBlocks<K, P>& hb, const ConstHCtx<K, P>& cx,
-                                            long long (&rowofs)[3], double (&yold)[3][K]) {
+                                            long long (&rowofs)[3]) {
     constexpr int NQ = 1 << P;
     if constexpr (Q < NQ) {
-        // prefetch old y of block-row Q + 2 (slots rotate modulo 3)
-        if constexpr (Q + 2 < NQ) {
+        if constexpr (Q + 2 < NQ) {          // row offsets two block-rows ahead (slots rotate modulo 3)
             const CellOfs co = cx.ctab_s[Q + 2];
             rowofs[(Q + 2) % 3] = co.bq + cx.u + co.kc * cx.v;
-            if (cx.accumulate && cx.ok) {
-#pragma unroll
-                for (int mo = 0; mo < K; ++mo) yold[(Q + 2) % 3][mo] = cx.Y[rowofs[(Q + 2) % 3] + cx.A * mo];
-            }
         }
         double acc[2][K];
 #pragma unroll
@@ -1205,10 +1194,11 @@ __device__ __forceinline__ void consth_rows(const HBlocks<K, P>& hb, const Const
 #pragma unroll
             for (int mo = 0; mo < K; ++mo) {
                 const double r = acc[0][mo] + acc[1][mo];
-                cx.Y[rowofs[Q % 3] + cx.A * mo] = cx.accumulate ? fma(cx.alpha, r, yold[Q % 3][mo]) : cx.alpha * r;
+                if (cx.accumulate) atomicAdd(&cx.Y[rowofs[Q % 3] + cx.A * mo], cx.alpha * r);      // RED.ADD.F64
+                else cx.Y[rowofs[Q % 3] + cx.A * mo] = cx.alpha * r;
             }
         }
-        consth_rows<K, P, Q + 1>(hb, cx, rowofs, yold);
+        consth_rows<K, P, Q + 1>(hb, cx, rowofs);
     }
 }
 
@@ -1265,23 +1255,14 @@ sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     cx.X = X; cx.Y = Y; cx.ctab_s = ctab_s; cx.u = u; cx.v = v; cx.alpha = alpha; cx.A = A;
     cx.ok = ok; cx.accumulate = accumulate != 0; cx.xs_s = xs_s;
     long long rowofs[3];
-    double yold[3][K];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int mo = 0; mo < K; ++mo) yold[i][mo] = 0.0;
-#pragma unroll
-    for (int r = 0; r < 2 && r < NQ; ++r) {          // rows 0 and 1: prefetched here, the rest two rows ahead
+    for (int r = 0; r < 2 && r < NQ; ++r) {          // rows 0 and 1 here, the rest two rows ahead
         const CellOfs co = ctab_s[r];
         rowofs[r] = co.bq + u + co.kc * v;
-        if (cx.accumulate && ok) {
-#pragma unroll
-            for (int mo = 0; mo < K; ++mo) yold[r][mo] = Y[rowofs[r] + A * mo];
-        }
     }
     cp_async_wait<0>();
     __syncwarp();
-    consth_rows<K, P, 0>(hb, cx, rowofs, yold);
+    consth_rows<K, P, 0>(hb, cx, rowofs);
     if (dbg && threadIdx.x == 0 && blockIdx.x < 512) {
         long long* o = dbg + 1024 + blockIdx.x * 4;
         o[0] = smid_u32(); o[1] = g_t0; o[2] = gtimer();

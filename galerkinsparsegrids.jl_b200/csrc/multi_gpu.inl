@@ -171,32 +171,48 @@ int mg_rhs_phase_a(gsg_mg& M, int wi, int ki, const double* c) {
     return 0;
 }
 
-// phase B: local sweeps, then the partition dimensions (straddling poles on the bit-0 rank, p == 0 poles on the bit-1 rank)
+// phase B: every sweep of the right-hand side through the concurrent scheduler -- the local directions start at
+// once (the first initialises k), the partition dimensions as soon as their level-0 cells have been pulled
+// (straddling poles on the bit-0 rank, p == 0 poles on the bit-1 rank); then the SWEPT signals
 int mg_rhs_phase_b(gsg_mg& M, int wi, int ki, const double* c) {
     gsg_plan& pl = *M.plan;
     const int D = pl.S.D;
     const double* w = M.vec(M.rank, wi);
     double* k = M.vec(M.rank, ki);
+    nvtx_range r("mg_rhs:sweeps");
+    static const bool serial = getenv("GSG_RHS_SERIAL") != nullptr;
+    if (!serial) {
+        cudaEvent_t pre[16] = {nullptr};
+        unsigned mask = 0;
+        for (int d = 0; d < D; ++d)
+            if (c[d] != 0.0) mask |= 1u << d;
+        for (size_t i = 0; i < M.ex.size(); ++i) {
+            gsg_mg::Ex& e = M.ex[i];
+            if (c[e.d] != 0.0 && e.mybit == 0 && e.ncells > 0) pre[e.d] = M.ev_x[i];
+        }
+        bool local_any = false;
+        for (int d = 0; d < D - M.bits; ++d) local_any = local_any || c[d] != 0.0;
+        if (!local_any) GSG_TRY(sweep(pl, 0, 0.0, w, 0.0, k));          // k starts from zero on the owned cells
+        GSG_TRY(rhs_concurrent(pl, c, mask, w, k, local_any ? 0.0 : 1.0, pre));
+        for (gsg_mg::Ex& e : M.ex)
+            if (c[e.d] != 0.0 && e.mybit == 0 && e.ncells > 0) GSG_TRY(mg_signal(M, pl.stream, e.partner, 1 + e.j, 0));
+        return 0;
+    }
     unsigned local_mask = 0;
     for (int d = 0; d < D - M.bits; ++d)
         if (c[d] != 0.0) local_mask |= 1u << d;
-    {
-        nvtx_range r("mg_rhs:local_sweeps");
-        if (local_mask == 0) {
-            // no local direction with a non-zero coefficient: k starts from zero on the owned cells
-            GSG_TRY(sweep(pl, 0, 0.0, w, 0.0, k));
-        } else if (can_fuse(pl, c, local_mask)) {
-            GSG_TRY(grad_fused(pl, c, w, k, local_mask, 0.0));
-        } else {
-            bool first = true;
-            for (int d = 0; d < D; ++d) {
-                if (!((local_mask >> d) & 1)) continue;
-                GSG_TRY(sweep(pl, d, c[d], w, first ? 0.0 : 1.0, k));
-                first = false;
-            }
+    if (local_mask == 0) {
+        GSG_TRY(sweep(pl, 0, 0.0, w, 0.0, k));
+    } else if (can_fuse(pl, c, local_mask)) {
+        GSG_TRY(grad_fused(pl, c, w, k, local_mask, 0.0));
+    } else {
+        bool first = true;
+        for (int d = 0; d < D; ++d) {
+            if (!((local_mask >> d) & 1)) continue;
+            GSG_TRY(sweep(pl, d, c[d], w, first ? 0.0 : 1.0, k));
+            first = false;
         }
     }
-    nvtx_range r("mg_rhs:partition_sweeps");
     for (size_t i = 0; i < M.ex.size(); ++i) {
         gsg_mg::Ex& e = M.ex[i];
         if (c[e.d] == 0.0) continue;

@@ -437,10 +437,13 @@ def test_ode_wave_2d_reference_assertions(gsg, oracle, order):
     st_g = {}
     tout, yout = gsg.ode_solve(plan, gsg.RHS_WAVE, np.concatenate([u0, np.zeros(N)]), [0.0, 1.0], order=order, stats=st_g)
     assert (st_g["accepted"], st_g["rejected"]) == (st_o["accepted"], st_o["rejected"])
-    assert len(tout) == len(t_ref) and np.abs(np.array(tout) - np.array(t_ref)).max() < 1e-12
+    # the step sizes come out of err^(-1/(order+1)) with err a norm of differences of nearly equal vectors: rounding
+    # noise of the operator form (device: D(Dx), oracle here: the reference's (D*D)x) moves them by ~1e-9 relative;
+    # the states at t = 1 still agree far below the integrator's own 1e-5 tolerance
+    assert len(tout) == len(t_ref) and np.abs(np.array(tout) - np.array(t_ref)).max() < 1e-7
     err = relerr(yout[-1], y_ref[-1])
     print(f"ode{order} 2-D wave: {st_g}, final state vs oracle {err:.3e}")
-    assert err <= TOL
+    assert err <= 1e-10
     times, E = gsg.energy_func(D, k, n, (tout, yout))
     assert 0 < E[0] - E[-1] < 1.0e-8
     assert np.all(np.abs(np.sqrt(E) - math.sqrt(2) * math.pi) < 1.0e-4)

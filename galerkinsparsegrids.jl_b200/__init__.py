@@ -23,7 +23,7 @@ __all__ = [
     "periodic_DLF_matrix", "coeffs_DG", "vcoeffs_DG", "tensor_construct", "V2D", "D2V", "V2Dref",
     "D2Vref", "D_matrix", "grad_matrix", "laplacian_matrix", "reconstruct_DG", "mcerr",
     "wave_evolve", "wave_evolve_1D", "advect_evolve", "energy_func", "energy_func_1D", "pos_vcoeffs_DG", "OdeIntegrator",
-    "ode_solve", "RHS_ADVECT", "RHS_WAVE", "RHS_CSR", "spmv_csc", "CsrMatrix", "device_info",
+    "ode_solve", "write_operators", "write_solution", "read_dump", "RHS_ADVECT", "RHS_WAVE", "RHS_CSR", "spmv_csc", "CsrMatrix", "device_info",
     "launch_count",
 ]
 
@@ -381,6 +381,21 @@ class Plan:
     def unpack_dev(self, dev_vec, ref_vec) -> None:
         check(lib.gsg_unpack_dev(self._h, _devptr(dev_vec), _devptr(ref_vec)))
 
+    def tensor_construct_dev(self, vcoeff_array, device=None):
+        """tensor_construct(D, k, n, [v_1..v_D]) expanded on the device: returns a zero-padded torch tensor in
+        device layout (src/tensor_construct.jl:19-63)."""
+        import torch
+        if len(vcoeff_array) != self.D:
+            raise ValueError("tensor_construct: need D coefficient vectors")
+        vs = [_f64(v) for v in vcoeff_array]
+        for v in vs:
+            if v.size != (self.k << self.n):
+                raise ValueError("tensor_construct: 1-D vectors must have length k*2^n")
+        arr = (C.c_void_p * self.D)(*[v.ctypes.data for v in vs])
+        out = torch.zeros(self.dev_size, dtype=torch.float64, device=device if device is not None else "cuda")
+        check(lib.gsg_tensor_construct_dev(self._h, arr, _devptr(out)))
+        return out
+
     def to_device(self, host_vec, device="cuda:0"):
         """numpy reference-layout vector -> zero-padded torch tensor in device layout."""
         import torch
@@ -709,6 +724,57 @@ def energy_func(D: int, k: int, n: int, soln, scheme: str = "sparse"):
     times, states = soln
     N = plan.size
     return np.array(times), np.array([plan.energy(s[:N], s[N:]) for s in states])
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk format (src/pdes.jl:145-163, 217-223)
+# ---------------------------------------------------------------------------------------------
+# The reference dumps its operators and solution snapshots into "vlasov.h5" through JLD2 with the dataset names
+#   dimensions, order, levels, "<name>.m", "<name>.n", "<name>.colptr", "<name>.rowval", "<name>.nzval"
+#   (name in m2n, n2p, p2n, n2m, "Ds[d]"; colptr / rowval 1-BASED Int64), times, "f_modal.%06d".
+# No HDF5 library is available in this image, so the container here is numpy's .npz with EXACTLY those dataset names
+# and conventions (1-based Int64 CSC fields, Float64 vectors): a post-processing script only swaps the file opener.
+def _csc_fields(name: str, A) -> dict:
+    import scipy.sparse as sp
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    return {f"{name}.m": np.int64(A.shape[0]), f"{name}.n": np.int64(A.shape[1]),
+            f"{name}.colptr": A.indptr.astype(np.int64) + 1, f"{name}.rowval": A.indices.astype(np.int64) + 1,
+            f"{name}.nzval": _f64(A.data)}
+
+
+def write_operators(path: str, D: int, k: int, n: int, operators: dict) -> None:
+    """jldopen(path, "w"): dimensions / order / levels + every matrix as the five SparseMatrixCSC fields."""
+    fields = {"dimensions": np.int64(D), "order": np.int64(k), "levels": np.int64(n)}
+    for name, A in operators.items():
+        fields.update(_csc_fields(name, A))
+    np.savez(path, **fields)
+
+
+def write_solution(path: str, soln) -> None:
+    """jldopen(path, "r+"): adds `times` and `f_modal.%06d` (1-based) to the file written by write_operators."""
+    times, states = soln
+    fields = dict(np.load(path)) if __import__("os").path.exists(path) else {}
+    fields["times"] = _f64(times)
+    for i, sol in enumerate(states, start=1):
+        fields["f_modal.%06d" % i] = _f64(sol)
+    np.savez(path, **fields)
+
+
+def read_dump(path: str):
+    """-> (meta, operators as scipy CSC, times, states) from a file written by the two functions above."""
+    import scipy.sparse as sp
+    z = np.load(path)
+    meta = {key: int(z[key]) for key in ("dimensions", "order", "levels") if key in z}
+    ops = {}
+    for key in z.files:
+        if key.endswith(".colptr"):
+            name = key[:-7]
+            ops[name] = sp.csc_matrix((z[f"{name}.nzval"], z[f"{name}.rowval"] - 1, z[f"{name}.colptr"] - 1),
+                                      shape=(int(z[f"{name}.m"]), int(z[f"{name}.n"])))
+    times = z["times"] if "times" in z else None
+    states = [z[key] for key in sorted(f for f in z.files if f.startswith("f_modal."))]
+    return meta, ops, times, states
 
 
 # ---------------------------------------------------------------------------------------------

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gsg_plan_destroy": (i32, [vp]),
     "gsg_plan_size": (i32, [vp, p_i64]),
     "gsg_plan_dev_size": (i32, [vp, p_i64]),
+    "gsg_tensor_construct_dev": (i32, [vp, C.POINTER(vp), vp]),
     "gsg_pack_dev": (i32, [vp, vp, vp]),
     "gsg_unpack_dev": (i32, [vp, vp, vp]),
     "gsg_plan_set_stream": (i32, [vp, vp]),

@@ -172,6 +172,8 @@ struct gsg_plan {
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t ev_fork = nullptr, ev_pair_fork = nullptr, ev_pair_done = nullptr;
 
+    DevBuf<int> cell_block;          // block of every multi-cell (device tensor_construct)
+    DevBuf<double> w1d;              // D concatenated 1-D coefficient vectors
     // reconstruct tables
     DevBuf<unsigned char> r_level;
     DevBuf<long long> r_offset;
@@ -184,8 +186,8 @@ struct gsg_plan {
     int ctr_next = 0;
     // concurrent right-hand side (rhs_concurrent): pool of high-priority streams for the long-pole launches of ALL
     // directions, forked after the first (beta = 0) pieces and joined at the end
-    std::vector<cudaStream_t> pool;
-    std::vector<cudaEvent_t> pool_ev;
+    std::vector<cudaStream_t> pool;        // [0, 16): high priority (long-pole launches); [16, 24): low priority
+    std::vector<cudaEvent_t> pool_ev;      //           (SM-filling persistent kernels: their ramp-up / drain overlap)
     cudaEvent_t ev_p1 = nullptr;
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
@@ -931,7 +933,9 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         int tb, tn;
         tile_range(pl, c.ntiles, tb, tn);
         if (tn == 0) return 0;
-        const int grid = std::min(tn, pl.sm_count);
+        // one CTA per SM; a launch with little work (a rank's share of a partitioned plan) takes fewer CTAs, >= 12 tiles
+        // each, so that the independent launches of a right-hand side run side by side instead of queueing for SMs
+        const int grid = std::max(1, std::min(pl.sm_count, std::min(tn, std::max(8, tn / 12))));
         static_assert(sizeof(HDense<K>) + 256 < 32000, "dense blocks must fit the kernel parameter space");
         HDense<K> hd;
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
@@ -971,7 +975,7 @@ int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y
         auto kern = sweep_stream_kernel<K, true>;
         static thread_local size_t configured = 0;
         GSG_TRY(ensure_smem(kern, c.smem, configured));
-        const int grid = std::min(c.ntiles, pl.sm_count);
+        const int grid = std::max(1, std::min(pl.sm_count, std::min(c.ntiles, std::max(8, c.ntiles / 12))));
         HDense<K> hd;
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
@@ -1236,18 +1240,19 @@ bool can_fuse(const gsg_plan& pl, const double* c, unsigned mask = ~0u) {
 struct PoolCtx {
     gsg_plan& pl;
     unsigned used = 0;
-    int next = 0;
+    int next = 0, next_lo = 0;
     explicit PoolCtx(gsg_plan& p) : pl(p) {}
-    int take(cudaStream_t* out, cudaEvent_t after, cudaEvent_t after2 = nullptr) {
-        const int i = next++ & 15;
+    int take_index(int i, cudaStream_t* out, cudaEvent_t after, cudaEvent_t after2) {
         if (!((used >> i) & 1u) && after) GSG_CUDA(cudaStreamWaitEvent(pl.pool[i], after, 0));
         if (after2) GSG_CUDA(cudaStreamWaitEvent(pl.pool[i], after2, 0));
         used |= 1u << i;
         *out = pl.pool[i];
         return 0;
     }
+    int take(cudaStream_t* out, cudaEvent_t after, cudaEvent_t after2 = nullptr) { return take_index(next++ & 15, out, after, after2); }
+    int take_lo(cudaStream_t* out, cudaEvent_t after, cudaEvent_t after2 = nullptr) { return take_index(16 + (next_lo++ & 7), out, after, after2); }
     int join() {
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 24; ++i)
             if ((used >> i) & 1u) {
                 GSG_CUDA(cudaEventRecord(pl.pool_ev[i], pl.pool[i]));
                 GSG_CUDA(cudaStreamWaitEvent(pl.stream, pl.pool_ev[i], 0));
@@ -1281,15 +1286,15 @@ int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x
         return j < npairs && ((mask >> da) & 1) && ((mask >> db) & 1) && c[da] != 0.0 && c[db] != 0.0 &&
                !(pre_wait && (pre_wait[da] || pre_wait[db]));
     };
-    auto do_pair = [&](int j, double beta) -> int {
+    auto do_pair = [&](int j, double beta, cudaStream_t st) -> int {
         if (pl.pairs[j].ntiles == 0) return 0;
         const int da = 2 * j, db = da + 1;
         switch (K) {
-            case 1: return launch_pair<1>(pl, pl.stream, j, x, y, c[da], c[db], beta);
-            case 2: return launch_pair<2>(pl, pl.stream, j, x, y, c[da], c[db], beta);
-            case 3: return launch_pair<3>(pl, pl.stream, j, x, y, c[da], c[db], beta);
-            case 4: return launch_pair<4>(pl, pl.stream, j, x, y, c[da], c[db], beta);
-            case 5: return launch_pair<5>(pl, pl.stream, j, x, y, c[da], c[db], beta);
+            case 1: return launch_pair<1>(pl, st, j, x, y, c[da], c[db], beta);
+            case 2: return launch_pair<2>(pl, st, j, x, y, c[da], c[db], beta);
+            case 3: return launch_pair<3>(pl, st, j, x, y, c[da], c[db], beta);
+            case 4: return launch_pair<4>(pl, st, j, x, y, c[da], c[db], beta);
+            case 5: return launch_pair<5>(pl, st, j, x, y, c[da], c[db], beta);
         }
         return fail(GSG_ERR_UNSUPPORTED, "internal: pair fusion for k > 5");
     };
@@ -1302,7 +1307,7 @@ int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x
             const int j = d / 2;
             if ((d & 1) == 0 && pair_fused(j)) {
                 first_pair = j;
-                GSG_TRY(do_pair(j, 0.0));
+                GSG_TRY(do_pair(j, 0.0, pl.stream));
                 GSG_TRY(sweep(pl, d, c[d], x, 0.0, y, true));
             } else if ((d & 1) == 1 && pair_fused(j)) {
                 continue;                      // (cannot happen: the even member comes first)
@@ -1334,11 +1339,22 @@ int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x
         GSG_TRY(sweep_scatter(pl, ctx, d, c[d], x, y, fused, pl.ev_p1, pre_wait ? pre_wait[d] : nullptr, deferred));
         for (size_t i = n0; i < deferred.size(); ++i) deferred_dir.push_back(d);
     }
-    for (int j : pairs_todo) GSG_TRY(do_pair(j, 1.0));
+    // SM-filling persistent kernels: one low-priority pool stream each, so that the drain of one overlaps the ramp-up
+    // of the next (GSG_RHS_ONE_STREAM: all on the main stream, in order)
+    static const bool one_stream_env = getenv("GSG_RHS_ONE_STREAM") != nullptr;
+    // (event-timed launches stay on the main stream: a start event on a side stream would also time the wait for SMs)
+    const bool one_stream = one_stream_env || (pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size()));
+    for (int j : pairs_todo) {
+        cudaStream_t st = pl.stream;
+        if (!one_stream) GSG_TRY(ctx.take_lo(&st, pl.ev_p1));
+        GSG_TRY(do_pair(j, 1.0, st));
+    }
     for (size_t i = 0; i < deferred.size(); ++i) {
         const int d = deferred_dir[i];
-        if (pre_wait && pre_wait[d]) GSG_CUDA(cudaStreamWaitEvent(pl.stream, pre_wait[d], 0));
-        GSG_TRY(launch_class(pl, pl.stream, *deferred[i].first, *deferred[i].second, x, y, c[d], 1.0));
+        cudaStream_t st = pl.stream;
+        if (!one_stream) GSG_TRY(ctx.take_lo(&st, pl.ev_p1, pre_wait ? pre_wait[d] : nullptr));
+        else if (pre_wait && pre_wait[d]) GSG_CUDA(cudaStreamWaitEvent(pl.stream, pre_wait[d], 0));
+        GSG_TRY(launch_class(pl, st, *deferred[i].first, *deferred[i].second, x, y, c[d], 1.0));
     }
     return ctx.join();
 }
@@ -1634,10 +1650,10 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
         GSG_CUDA(cudaEventCreateWithFlags(&P->ev_done[i], cudaEventDisableTiming));
     }
     GSG_TRY(P->tile_counter.resize(64));
-    P->pool.assign(16, nullptr);
-    P->pool_ev.assign(16, nullptr);
-    for (int i = 0; i < 16; ++i) {
-        GSG_CUDA(cudaStreamCreateWithPriority(&P->pool[i], cudaStreamNonBlocking, prio_hi));
+    P->pool.assign(24, nullptr);
+    P->pool_ev.assign(24, nullptr);
+    for (int i = 0; i < 24; ++i) {
+        GSG_CUDA(cudaStreamCreateWithPriority(&P->pool[i], cudaStreamNonBlocking, i < 16 ? prio_hi : prio_lo));
         GSG_CUDA(cudaEventCreateWithFlags(&P->pool_ev[i], cudaEventDisableTiming));
     }
     GSG_CUDA(cudaEventCreateWithFlags(&P->ev_p1, cudaEventDisableTiming));
@@ -2066,6 +2082,38 @@ int gsg_energy(gsg_plan* plan, const double* u, const double* udot, double* ener
     g_launches.fetch_add(pl.S.D + 1, std::memory_order_relaxed);
     GSG_CUDA(cudaMemcpyAsync(energy_out, pl.wred.p, sizeof(double), cudaMemcpyDeviceToHost, pl.stream));
     GSG_CUDA(cudaStreamSynchronize(pl.stream));
+    return 0;
+}
+
+// ---- tensor_construct on the device ----------------------------------------------------------------------
+// out_dev (DEVICE layout, length gsg_plan_dev_size; padding slots untouched) = tensor_construct(D, k, n, [v_1..v_D])
+// from D host vectors of length k*2^n: what every D >= 3 example builds its initial data with
+// (examples/traveling_wave.jl:18-48, examples/vlasov_evolve.jl:27) -- one small upload + one expansion kernel
+// instead of an N-entry host loop and a 276 MB copy.
+int gsg_tensor_construct_dev(gsg_plan* plan, const double* const* vcoeffs_1d, double* out_dev) {
+    GSG_TRY(check_plan(plan));
+    if (!vcoeffs_1d || !out_dev) return fail(GSG_ERR_ARG, "null pointer");
+    gsg_plan& pl = *plan;
+    const gsg::IndexSet& S = pl.S;
+    const int n1d = S.k << S.n;
+    if (!pl.cell_block.p) {
+        std::vector<int> cb((size_t)S.ncells_total);
+        size_t c = 0;
+        for (size_t b = 0; b < S.blocks.size(); ++b)
+            for (int64_t i = 0; i < S.blocks[b].ncells; ++i) cb[c++] = (int)b;
+        GSG_TRY(pl.cell_block.upload(cb));
+    }
+    GSG_TRY(pl.w1d.resize((size_t)S.D * n1d));
+    for (int d = 0; d < S.D; ++d) {
+        if (!vcoeffs_1d[d]) return fail(GSG_ERR_ARG, "null 1-D coefficient vector");
+        GSG_CUDA(cudaMemcpyAsync(pl.w1d.p + (size_t)d * n1d, vcoeffs_1d[d], sizeof(double) * n1d, cudaMemcpyHostToDevice, pl.stream));
+    }
+    const int grid = (int)std::min<int64_t>(S.ncells_total, (int64_t)pl.sm_count * 16);
+    tensor_construct_kernel<<<grid, 256, 0, pl.stream>>>(pl.cell_block.p, S.ncells_total, pl.r_level.p, pl.r_offset.p, pl.w1d.p,
+                                                          S.D, S.k, n1d, (int)S.kD, (int)S.kDp, out_dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GSG_CUDA(cudaGetLastError());
+    GSG_CUDA(cudaStreamSynchronize(pl.stream));       // the host vectors may be pageable: do not return before the copies
     return 0;
 }
 

@@ -1362,6 +1362,46 @@ __global__ void sumsq_kernel(long long N, const double* __restrict__ x, double* 
 }
 
 // ------------------------------------------------------------------------------------------
+// tensor_construct on the device (src/tensor_construct.jl:19-63, vector overload): the coefficient of
+// prod_d f_d(x_d) on the sparse index set is the product of the 1-D coefficients, `val = one(T); for d in 1:D
+// val *= coeff[d][l_d][c_d][m_d]` (same multiplication order: bit-identical to the host version).
+// One CTA per multi-cell (grid-stride); v1d = D concatenated 1-D vectors of length K * 2^n in vector layout.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tensor_construct_kernel(const int* __restrict__ cell_block, long long ncells, const unsigned char* __restrict__ blk_level,
+                        const long long* __restrict__ blk_poffset, const double* __restrict__ v1d, int D, int k, int n1d,
+                        int KD, int KDp, double* __restrict__ out) {
+    __shared__ int base1d[16];          // k * (first cell of level l_d + c_d): index of mode 0 in the 1-D vector
+    for (long long ci = blockIdx.x; ci < ncells; ci += gridDim.x) {
+        const int b = cell_block[ci];
+        const long long poff = blk_poffset[b];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long rem = ci - poff / KDp;      // cell index inside the block, first dimension fastest
+            for (int d = 0; d < D; ++d) {
+                const int l = blk_level[(size_t)b * D + d];
+                const int cells = l <= 1 ? 1 : 1 << (l - 1);
+                const int c = (int)(rem % cells);
+                rem /= cells;
+                base1d[d] = k * ((l == 0 ? 0 : 1 << (l - 1)) + c);
+            }
+        }
+        __syncthreads();
+        double* dst = out + ci * KDp;
+        for (int e = threadIdx.x; e < KD; e += blockDim.x) {
+            int r = e;
+            double val = 1.0;
+            for (int d = 0; d < D; ++d) {
+                const int m = r % k;
+                r /= k;
+                val = __dmul_rn(val, v1d[(size_t)d * n1d + base1d[d] + m]);
+            }
+            dst[e] = val;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Batched reconstruct_DG (src/dg_methods.jl:150-165): one warp per point.
 //   1. the warp fills a per-point table of the D*(n+1)*K one-dimensional basis values
 //      v(k, l, cell(x_i,l), m, x_i) and the cell indices (src/dg_methods.jl:27-36,70-79);

@@ -73,11 +73,20 @@ mg_pull_add_kernel(const int* __restrict__ cells, long long ncells, int KDp, dou
         double2* dst = reinterpret_cast<double2*>(k_local + base);
         for (int e = threadIdx.x; e < n2; e += blockDim.x) {
             const double2 a = src[e];
-            double2 b = dst[e];
-            b.x += a.x;
-            b.y += a.y;
-            dst[e] = b;
+            // reductions at the L2: the pull-adds of different partition dimensions overlap in cells and in time
+            atomicAdd(reinterpret_cast<double*>(dst + e), a.x);
+            atomicAdd(reinterpret_cast<double*>(dst + e) + 1, a.y);
         }
+    }
+}
+
+// y[cell] = 0 on the listed multi-cells
+__global__ void __launch_bounds__(256)
+mg_zero_cells_kernel(const int* __restrict__ cells, long long ncells, int KDp, double* __restrict__ y) {
+    const int n2 = KDp >> 1;
+    for (long long ci = blockIdx.x; ci < ncells; ci += gridDim.x) {
+        double2* dst = reinterpret_cast<double2*>(y + (long long)cells[ci] * KDp);
+        for (int e = threadIdx.x; e < n2; e += blockDim.x) dst[e] = make_double2(0.0, 0.0);
     }
 }
 
@@ -190,10 +199,20 @@ int mg_rhs_phase_b(gsg_mg& M, int wi, int ki, const double* c) {
             gsg_mg::Ex& e = M.ex[i];
             if (c[e.d] != 0.0 && e.mybit == 0 && e.ncells > 0) pre[e.d] = M.ev_x[i];
         }
-        bool local_any = false;
-        for (int d = 0; d < D - M.bits; ++d) local_any = local_any || c[d] != 0.0;
-        if (!local_any) GSG_TRY(sweep(pl, 0, 0.0, w, 0.0, k));          // k starts from zero on the owned cells
-        GSG_TRY(rhs_concurrent(pl, c, mask, w, k, local_any ? 0.0 : 1.0, pre));
+        // k = 0 on the owned cells (1/nranks of the state), then EVERY sweep accumulates: no piece has to finish
+        // before the others may start (a single rank initialises k with its first sweep instead: no extra pass)
+        static const bool zero_first = !getenv("GSG_MG_NO_ZERO");
+        if (M.nranks > 1 && zero_first && M.n_owned > 0) {
+            const int grid = (int)std::min<int64_t>(M.n_owned, (int64_t)pl.sm_count * 8);
+            mg_zero_cells_kernel<<<grid, 256, 0, pl.stream>>>(M.owned_cells.p, M.n_owned, (int)pl.S.kDp, k);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GSG_TRY(rhs_concurrent(pl, c, mask, w, k, 1.0, pre));
+        } else {
+            bool local_any = false;
+            for (int d = 0; d < D - M.bits; ++d) local_any = local_any || c[d] != 0.0;
+            if (!local_any) GSG_TRY(sweep(pl, 0, 0.0, w, 0.0, k));          // k starts from zero on the owned cells
+            GSG_TRY(rhs_concurrent(pl, c, mask, w, k, local_any ? 0.0 : 1.0, pre));
+        }
         for (gsg_mg::Ex& e : M.ex)
             if (c[e.d] != 0.0 && e.mybit == 0 && e.ncells > 0) GSG_TRY(mg_signal(M, pl.stream, e.partner, 1 + e.j, 0));
         return 0;
@@ -224,20 +243,25 @@ int mg_rhs_phase_b(gsg_mg& M, int wi, int ki, const double* c) {
     return 0;
 }
 
-// phase C: pull-add the partners' contributions to my level-0 cells; then k is final
+// phase C: pull-add the partners' contributions to my level-0 cells (each partition dimension on its own pool
+// stream: wait for the partner's SWEPT, then reduce its scratch cells into mine); then k is final
 int mg_rhs_phase_c(gsg_mg& M, int ki, const double* c, bool signal_ready) {
     gsg_plan& pl = *M.plan;
     nvtx_range r("mg_rhs:pull_add");
+    GSG_CUDA(cudaEventRecord(pl.ev_p1, pl.stream));
+    PoolCtx ctx(pl);
     for (size_t i = 0; i < M.ex.size(); ++i) {
         gsg_mg::Ex& e = M.ex[i];
         if (e.mybit != 1 || e.ncells == 0 || c[e.d] == 0.0) continue;
-        GSG_TRY(mg_wait(M, pl.stream, e.partner, 1 + e.j, 0));
+        cudaStream_t st;
+        GSG_TRY(ctx.take(&st, pl.ev_p1));
+        GSG_TRY(mg_wait(M, st, e.partner, 1 + e.j, 0));
         const int grid = (int)std::min<int64_t>(e.ncells, (int64_t)pl.sm_count * 8);
-        mg_pull_add_kernel<<<grid, 256, 0, pl.stream>>>(e.cells.p, e.ncells, (int)pl.S.kDp, M.vec(M.rank, ki),
-                                                         M.vec(e.partner, ki));
+        mg_pull_add_kernel<<<grid, 256, 0, st>>>(e.cells.p, e.ncells, (int)pl.S.kDp, M.vec(M.rank, ki), M.vec(e.partner, ki));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         GSG_CUDA(cudaGetLastError());
     }
+    GSG_TRY(ctx.join());
     if (signal_ready) {
         for (gsg_mg::Ex& e : M.ex)
             if (e.mybit == 1 && e.ncells > 0) GSG_TRY(mg_signal(M, pl.stream, e.partner, 0, 1));    // READY = next RHS

@@ -75,6 +75,7 @@ int gsg_tensor_construct(int D, int k, int n, int scheme, const double* const* v
                          double* out);
 
 /* ---- plan ----------------------------------------------------------------------------- */
+/* (declared further down: gsg_tensor_construct_dev builds tensor_construct's result directly in a device vector) */
 /* Replaces the construction of grad_matrix / laplacian_matrix (src/pdes.jl:59,141;
  * src/multidim_derivative.jl:19-79).  H = periodic_DLF_matrix(k, n) is handed over verbatim
  * (SURVEY.md headline fact 4: values as stored, noise entries included). */
@@ -88,6 +89,9 @@ int gsg_plan_size(const gsg_plan* plan, int64_t* size_out);
  * is that padded length; pack/unpack convert device-resident vectors (asynchronously on the
  * plan's stream); the padding slots of a device vector must be zero-initialised. */
 int gsg_plan_dev_size(const gsg_plan* plan, int64_t* size_out);
+/* tensor_construct(D, k, n, [v_1..v_D]) expanded ON THE DEVICE into out_dev (device layout; padding slots are left
+ * untouched: zero-initialise the vector once).  vcoeffs_1d: D HOST vectors of length k*2^n.  src/tensor_construct.jl:19-63 */
+int gsg_tensor_construct_dev(gsg_plan* plan, const double* const* vcoeffs_1d, double* out_dev);
 int gsg_pack_dev(gsg_plan* plan, const double* ref_layout_dev, double* dev_layout_dev);
 int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_layout_dev);
 /* run all subsequent work of this plan on `stream` (cudaStream_t); NULL = the plan's own */

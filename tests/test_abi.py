@@ -138,3 +138,22 @@ def test_structural_block_pattern_matches_oracle_H(gsg, oracle, k, n):
     cols = np.repeat(np.arange(H.n), np.diff(H.colptr))
     stored[np.asarray(H.rowval) // k, cols // k] = True
     assert np.array_equal(gsg.block_pattern(n), stored)
+
+
+def test_on_disk_dump_round_trip(gsg, tmp_path):
+    """The reference's dump layout (src/pdes.jl:145-163, 217-223): dataset names and 1-based CSC fields survive a
+    round trip; the stored operator is the library's own H."""
+    import scipy.sparse as sp
+    H = gsg.periodic_DLF_matrix(3, 3)
+    path = str(tmp_path / "vlasov.npz")
+    gsg.write_operators(path, 2, 3, 3, {"m2n": H, "Ds[1]": sp.identity(5, format="csc")})
+    z = np.load(path)
+    assert int(z["dimensions"]) == 2 and int(z["order"]) == 3 and int(z["levels"]) == 3
+    assert z["m2n.colptr"][0] == 1 and z["m2n.rowval"].min() >= 1 and z["m2n.colptr"].dtype == np.int64
+    states = [np.arange(4.0), np.arange(4.0) * 2]
+    gsg.write_solution(path, (np.array([0.0, 0.5]), states))
+    meta, ops, times, got = gsg.read_dump(path)
+    assert meta == {"dimensions": 2, "order": 3, "levels": 3}
+    assert (ops["m2n"] != H).nnz == 0 and ops["Ds[1]"].shape == (5, 5)
+    assert list(times) == [0.0, 0.5] and all(np.array_equal(a, b) for a, b in zip(got, states))
+    assert sorted(k for k in np.load(path).files if k.startswith("f_modal")) == ["f_modal.000001", "f_modal.000002"]

@@ -498,3 +498,15 @@ def test_ode_advect_specified_points(gsg, oracle, cb):
     with pytest.raises(ValueError):
         gsg.wave_evolve(D, k, n, u0, u0, 0.0, 1.0, order="23")
     plan.close()
+
+
+def test_tensor_construct_on_device(gsg, oracle):
+    """gsg_tensor_construct_dev: bit-identical to the host tensor_construct (src/tensor_construct.jl:19-63)."""
+    for D, k, n in [(2, 3, 5), (3, 2, 4), (4, 3, 4), (6, 3, 3)]:
+        plan = gsg.get_plan(D, k, n)
+        vs = [oracle.coeffs_1d(k, n, f) for f in (f_sin, f_gauss, f_cos)]
+        arr = [vs[d % 3] for d in range(D)]
+        ref = oracle.tensor_construct(D, k, n, arr)
+        dev = plan.tensor_construct_dev(arr)
+        assert np.array_equal(plan.to_host(dev), ref)
+        assert float(dev.sum()) == float(dev.sum())          # padding stayed finite (zero)

@@ -5,8 +5,7 @@ try:
 except Exception as e: print("$name failed", e); print(open("gpurun_out/exp3_$name.err").read()[-600:])
 PY
 }
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -s 2>&1 | grep -E "^E  |passed|failed|FAILED|vs oracle|vs assembled|RK4 x|ode4|ode7" | head -40
-run conc A=1
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "fused_gradient or config4 or mg_ or rk4 or ode" 2>&1 | grep -E "passed|failed|FAILED" | head
+run conc2 A=1
+run conc2_onestream GSG_RHS_ONE_STREAM=1
 run serial GSG_RHS_SERIAL=1
-run conc_rs8 GSG_LONG_RSPLIT=8
-run conc_noprio GSG_NO_PRIO=1

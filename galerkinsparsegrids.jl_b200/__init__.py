@@ -23,7 +23,7 @@ __all__ = [
     "periodic_DLF_matrix", "coeffs_DG", "vcoeffs_DG", "tensor_construct", "V2D", "D2V", "V2Dref",
     "D2Vref", "D_matrix", "grad_matrix", "laplacian_matrix", "reconstruct_DG", "mcerr",
     "wave_evolve", "wave_evolve_1D", "advect_evolve", "energy_func", "energy_func_1D", "pos_vcoeffs_DG", "OdeIntegrator",
-    "ode_solve", "write_operators", "write_solution", "read_dump", "RHS_ADVECT", "RHS_WAVE", "RHS_CSR", "spmv_csc", "CsrMatrix", "device_info",
+    "ode_solve", "VlasovRHS", "vlasov_evolve", "RHS_VLASOV", "write_operators", "write_solution", "read_dump", "RHS_ADVECT", "RHS_WAVE", "RHS_CSR", "spmv_csc", "CsrMatrix", "device_info",
     "launch_count",
 ]
 
@@ -540,7 +540,7 @@ def _steps(time0: float, time1: float, dt: float):
     return nsteps, (time1 - time0) / nsteps
 
 
-RHS_ADVECT, RHS_WAVE, RHS_CSR = 0, 1, 2
+RHS_ADVECT, RHS_WAVE, RHS_CSR, RHS_VLASOV = 0, 1, 2, 3
 
 
 class OdeIntegrator:
@@ -548,17 +548,21 @@ class OdeIntegrator:
     5(4)) / ode78 (Fehlberg 7(8)) calls of src/pdes.jl:62-68, 113-119, 206-213."""
 
     def __init__(self, plan: "Plan", rhs_kind: int, y0, t0: float, t1: float, order: str = "45", a=None, A=None,
-                 reltol: float = 0.0, abstol: float = 0.0):
+                 reltol: float = 0.0, abstol: float = 0.0, vlasov=None):
         if order not in ("45", "78"):
             raise ValueError("ArgumentError(:order)")
-        self.plan, self.A = plan, A                      # keep the matrix alive
+        self.plan, self.A, self.vlasov = plan, A, vlasov     # keep the matrix / right-hand side alive
         y0 = _f64(y0)
         self.n = y0.size
         a_arr = _f64(a) if a is not None else None
         h = C.c_void_p()
-        check(lib.gsg_ode_create(plan._h, rhs_kind, _ptr(a_arr) if a_arr is not None else None,
-                                 A._h if A is not None else None, int(order), float(reltol), float(abstol), _ptr(y0),
-                                 float(t0), float(t1), C.byref(h)))
+        if rhs_kind == RHS_VLASOV:
+            check(lib.gsg_ode_create_vlasov(vlasov._h, int(order), float(reltol), float(abstol), _ptr(y0), float(t0),
+                                            float(t1), C.byref(h)))
+        else:
+            check(lib.gsg_ode_create(plan._h, rhs_kind, _ptr(a_arr) if a_arr is not None else None,
+                                     A._h if A is not None else None, int(order), float(reltol), float(abstol), _ptr(y0),
+                                     float(t0), float(t1), C.byref(h)))
         self._h = h
         self.t, self.done = float(t0), False
 
@@ -597,12 +601,12 @@ class OdeIntegrator:
 
 
 def ode_solve(plan: "Plan", rhs_kind: int, y0, tspan, order: str = "45", points: str = "all", a=None, A=None,
-              reltol: float = 0.0, abstol: float = 0.0, stats: dict | None = None):
+              reltol: float = 0.0, abstol: float = 0.0, stats: dict | None = None, vlasov=None):
     """`ode45(F, y0, tspan; points)` / `ode78(...)` of ODE.jl on the device: returns (tout, yout) as ODE.jl does --
     points="all": every accepted step plus the requested times strictly inside a step (Hermite); points="specified":
     the requested times only (src/pdes.jl:207-213 uses this with range(t0, t1, length=nout))."""
     tspan = [float(t) for t in tspan]
-    ode = OdeIntegrator(plan, rhs_kind, y0, tspan[0], tspan[-1], order, a=a, A=A, reltol=reltol, abstol=abstol)
+    ode = OdeIntegrator(plan, rhs_kind, y0, tspan[0], tspan[-1], order, a=a, A=A, reltol=reltol, abstol=abstol, vlasov=vlasov)
     tdir = 1.0 if tspan[-1] > tspan[0] else -1.0
     tout, yout = [tspan[0]], [_f64(y0).copy()]
     if points == "specified":
@@ -652,6 +656,64 @@ def wave_evolve(D: int, k: int, n: int, f0coeffs, v0coeffs, time0: float, time1:
         u, v = plan.rk4_wave(u, v, h, ns)
         states.append(np.concatenate([u, v]))
     return times, states
+
+
+class VlasovRHS:
+    """`steprule` of vlasov_evolve (src/pdes.jl:174-192) resident on the device (gsg_vlasov_*)."""
+
+    def __init__(self, plan: "Plan", m2n, n2p, p2n, n2m, F_point):
+        self.plan = plan
+        self.mats = [A if isinstance(A, CsrMatrix) else CsrMatrix(A) for A in (m2n, n2p, p2n, n2m)]
+        Fs = [_f64(F) for F in F_point]
+        if len(Fs) != plan.D // 2 or any(F.shape != (plan.size,) for F in Fs):
+            raise ValueError("DimensionMismatch: F_point must hold D vectors of length N")
+        arr = (C.c_void_p * len(Fs))(*[F.ctypes.data for F in Fs])
+        h = C.c_void_p()
+        check(lib.gsg_vlasov_create(plan._h, *[A._h for A in self.mats], arr, C.byref(h)))
+        self._h = h
+
+    def __call__(self, t, f_modal) -> np.ndarray:
+        f = self.plan._vec(f_modal)
+        out = np.empty_like(f)
+        check(lib.gsg_vlasov_rhs(self._h, _ptr(f), _ptr(out)))
+        return out
+
+    def v_point(self, i: int) -> np.ndarray:
+        out = np.empty(self.plan.size)
+        check(lib.gsg_vlasov_v_point(self._h, int(i), _ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.gsg_vlasov_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vlasov_evolve(D: int, k: int, n: int, m2n, n2p, p2n, n2m, f0_modal, F_point, time0: float, time1: float,
+                  nout: int = 2, order: str = "45", scheme: str = "sparse", dump: str | None = None, **kwargs):
+    """vlasov_evolve(D, k, n, m2n, n2p, p2n, n2m, f0_modal, F_point, t0, t1, nout; order, scheme) -- src/pdes.jl:131-227.
+    The four transform matrices are inputs, as in the reference (scipy sparse, or resident CsrMatrix handles); the
+    right-hand side and the adaptive integrator run on the device; outputs at range(t0, t1, length=nout) when
+    points="specified" (what examples/vlasov_evolve.jl asks for).  `dump`: write the reference's operator / solution
+    file layout (write_operators / write_solution) to this path."""
+    if order not in ("45", "78"):
+        raise ValueError("ArgumentError(:order)")
+    plan = get_plan(2 * D, k, n, scheme)
+    rhs = VlasovRHS(plan, m2n, n2p, p2n, n2m, F_point)
+    tspan = np.linspace(time0, time1, nout)
+    soln = ode_solve(plan, RHS_VLASOV, f0_modal, tspan, order=order, vlasov=rhs, **kwargs)
+    if dump:
+        ops = {"m2n": m2n, "n2p": n2p, "p2n": p2n, "n2m": n2m}
+        write_operators(dump, D, k, n, {name: A for name, A in ops.items() if not isinstance(A, CsrMatrix)})
+        write_solution(dump, soln)
+    rhs.close()
+    return soln
 
 
 def pos_vcoeffs_DG(k: int, max_level: int, f, npts: int = 20) -> np.ndarray:

@@ -79,6 +79,11 @@ SIGNATURES = {
     "gsg_ode_state": (i32, [vp, vp]),
     "gsg_ode_interp": (i32, [vp, f64, vp]),
     "gsg_ode_stats": (i32, [vp, p_i64, p_i64, p_i64]),
+    "gsg_vlasov_create": (i32, [vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]),
+    "gsg_vlasov_destroy": (i32, [vp]),
+    "gsg_vlasov_rhs": (i32, [vp, vp, vp]),
+    "gsg_vlasov_v_point": (i32, [vp, i32, vp]),
+    "gsg_ode_create_vlasov": (i32, [vp, i32, f64, f64, vp, f64, f64, C.POINTER(vp)]),
     "gsg_mg_create": (i32, [vp, i32, i32, C.POINTER(vp)]),
     "gsg_mg_destroy": (i32, [vp]),
     "gsg_mg_ipc_handle": (i32, [vp, vp]),

@@ -2275,4 +2275,5 @@ int gsg_spmv_csc(int64_t m, int64_t n, const int64_t* colptr, const int64_t* row
 }  // extern "C"
 
 #include "multi_gpu.inl"
+#include "vlasov.inl"
 #include "ode.inl"

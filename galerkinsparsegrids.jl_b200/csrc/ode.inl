@@ -189,6 +189,7 @@ void ode_fill_tableau(OdeTableau& T, int method) {
 struct gsg_ode {
     gsg_plan* plan = nullptr;
     gsg_csr* A = nullptr;
+    gsg_vlasov* V = nullptr;
     int kind = 0;
     std::vector<double> a;                  // advection coefficients
     OdeTableau T;
@@ -223,6 +224,7 @@ int ode_rhs(gsg_ode& O, const double* w, double* k) {
             return laplacian(pl, w, k + Np, pl.wtmp.p);
         }
         case GSG_RHS_CSR: return gsg_csr_apply_dev(O.A, w, k, pl.stream);
+        case GSG_RHS_VLASOV: return vlasov_rhs_dev(*O.V, w, k);
     }
     return fail(GSG_ERR_ARG, "bad right-hand-side kind");
 }
@@ -319,18 +321,21 @@ int ode_attempt(gsg_ode& O, double* err_out, bool* nan_out) {
 
 extern "C" {
 
-int gsg_ode_create(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, int method, double reltol, double abstol,
-                   const double* y0_host, double t0, double t1, gsg_ode** out) {
+static int ode_create_impl(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, gsg_vlasov* V, int method, double reltol,
+                           double abstol, const double* y0_host, double t0, double t1, gsg_ode** out) {
     GSG_TRY(check_plan(plan));
     if (!out || !y0_host) return fail(GSG_ERR_ARG, "null pointer");
     if (method != 45 && method != 78) return fail(GSG_ERR_ARG, "ArgumentError(:order): method must be 45 or 78");
     if (!(t1 != t0)) return fail(GSG_ERR_ARG, "Zero time span");
     if (rhs_kind == GSG_RHS_ADVECT && !a) return fail(GSG_ERR_ARG, "advection coefficients required");
     if (rhs_kind == GSG_RHS_CSR && (!A || A->m != A->n)) return fail(GSG_ERR_ARG, "square resident matrix required");
-    if (rhs_kind != GSG_RHS_ADVECT && rhs_kind != GSG_RHS_WAVE && rhs_kind != GSG_RHS_CSR) return fail(GSG_ERR_ARG, "bad right-hand-side kind");
+    if (rhs_kind == GSG_RHS_VLASOV && !V) return fail(GSG_ERR_ARG, "vlasov handle required");
+    if (rhs_kind != GSG_RHS_ADVECT && rhs_kind != GSG_RHS_WAVE && rhs_kind != GSG_RHS_CSR && rhs_kind != GSG_RHS_VLASOV)
+        return fail(GSG_ERR_ARG, "bad right-hand-side kind");
     std::unique_ptr<gsg_ode> O(new gsg_ode());
     O->plan = plan;
     O->A = A;
+    O->V = V;
     O->kind = rhs_kind;
     if (a) O->a.assign(a, a + plan->S.D);
     ode_fill_tableau(O->T, method);
@@ -366,6 +371,19 @@ int gsg_ode_create(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, in
     GSG_TRY(ode_hinit(*O));
     *out = O.release();
     return 0;
+}
+
+int gsg_ode_create(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, int method, double reltol, double abstol,
+                   const double* y0_host, double t0, double t1, gsg_ode** out) {
+    if (rhs_kind == GSG_RHS_VLASOV) return fail(GSG_ERR_ARG, "use gsg_ode_create_vlasov");
+    return ode_create_impl(plan, rhs_kind, a, A, nullptr, method, reltol, abstol, y0_host, t0, t1, out);
+}
+
+// f' = steprule(t, f): the integrator call of vlasov_evolve (src/pdes.jl:206-213)
+int gsg_ode_create_vlasov(gsg_vlasov* v, int method, double reltol, double abstol, const double* f0_modal, double t0,
+                          double t1, gsg_ode** out) {
+    if (!v) return fail(GSG_ERR_ARG, "null vlasov handle");
+    return ode_create_impl(v->plan, GSG_RHS_VLASOV, nullptr, nullptr, v, method, reltol, abstol, f0_modal, t0, t1, out);
 }
 
 int gsg_ode_destroy(gsg_ode* ode) {

@@ -163,6 +163,7 @@ typedef struct gsg_ode gsg_ode;
 #define GSG_RHS_ADVECT 0      /* y' = -sum_d a[d] D_d y          state length N   (the operator of src/pdes.jl:179-180) */
 #define GSG_RHS_WAVE 1        /* [u; v]' = [v; L u]              state length 2N  (wave_data, src/pdes.jl:22-49)        */
 #define GSG_RHS_CSR 2         /* y' = A y, A a resident gsg_csr  state length A.m (wave_evolve_1D's RHS, src/pdes.jl:109-114) */
+#define GSG_RHS_VLASOV 3      /* f' = steprule(t, f)             state length N   (src/pdes.jl:174-192; gsg_ode_create_vlasov) */
 /* method: 45 or 78; reltol / abstol <= 0 select ODE.jl's defaults; `a` only for GSG_RHS_ADVECT, `A` only for GSG_RHS_CSR */
 int gsg_ode_create(gsg_plan* plan, int rhs_kind, const double* a, gsg_csr* A, int method, double reltol, double abstol,
                    const double* y0_host, double t0, double t1, gsg_ode** out);
@@ -171,6 +172,21 @@ int gsg_ode_step(gsg_ode* ode, double* t_out, double* dt_out, int* done_out);
 int gsg_ode_state(gsg_ode* ode, double* y_host);
 int gsg_ode_interp(gsg_ode* ode, double tquery, double* y_host);
 int gsg_ode_stats(gsg_ode* ode, int64_t* accepted, int64_t* rejected, int64_t* rhs_evals);
+
+/* ---- Vlasov right-hand side (src/pdes.jl:165-192) -----------------------------------------------------------------
+ * steprule(t, f) = n2m * (p2n * (-sum_d v_point[d] .* (n2p*(m2n*(Ds[d]*f))) + sum_d F_point[d] .* (n2p*(m2n*(Ds[D+d]*f)))))
+ * on the device: Ds[d]*f are the plan's matrix-free sweeps (plan = the (2D, k, n) operator), the four transform
+ * matrices are the ones the host passes to vlasov_evolve (resident gsg_csr handles), the products with v_point /
+ * F_point are fused pointwise kernels.  F_point: D host vectors of length N (point basis). */
+typedef struct gsg_vlasov gsg_vlasov;
+int gsg_vlasov_create(gsg_plan* plan, gsg_csr* m2n, gsg_csr* n2p, gsg_csr* p2n, gsg_csr* n2m,
+                      const double* const* F_point, gsg_vlasov** out);
+int gsg_vlasov_destroy(gsg_vlasov* v);
+int gsg_vlasov_rhs(gsg_vlasov* v, const double* f_modal, double* out);
+int gsg_vlasov_v_point(gsg_vlasov* v, int i, double* out);
+/* `solver(steprule, f0_modal, range(t0, t1, length = nout))`  src/pdes.jl:206-213 */
+int gsg_ode_create_vlasov(gsg_vlasov* v, int method, double reltol, double abstol, const double* f0_modal, double t0,
+                          double t1, gsg_ode** out);
 
 /* ---- multi-GPU RK4 inside the library: peer-mapped state slabs, no NCCL on the data path ---------------------
  * One gsg_mg per rank (one process per GPU, or several ranks inside one process).  gsg_mg_create partitions the

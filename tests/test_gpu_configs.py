@@ -510,3 +510,63 @@ def test_tensor_construct_on_device(gsg, oracle):
         dev = plan.tensor_construct_dev(arr)
         assert np.array_equal(plan.to_host(dev), ref)
         assert float(dev.sum()) == float(dev.sum())          # padding stayed finite (zero)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Vlasov right-hand side and evolution (src/pdes.jl:131-227) with real transform matrices from the nodal oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def vlasov_setup(gsg, oracle):
+    import nodal_oracle as no
+    D, k, n = 2, 3, 3                     # 4-D phase space
+    m2n, n2p = no.make_modal2point_matrices(2 * D, k, n)
+    p2n, n2m = no.make_point2modal_matrices(2 * D, k, n)
+    F_point = no.example_force_point(D, k, n, m2n, n2p)
+    gx = oracle.coeffs_1d(k, n, lambda x: math.exp(-2 * math.pi ** 2 * (x - 0.5) ** 2))
+    gv = oracle.coeffs_1d(k, n, lambda x: math.exp(-2 * math.pi ** 2 * x ** 2))
+    f0 = 2 * math.pi * oracle.tensor_construct(2 * D, k, n, [gx, gx, gv, gv])       # examples/vlasov_evolve.jl:20-27
+    H = oracle.periodic_DLF_matrix(k, n)
+    Ds = [oracle.D_matrix_poles(2 * D, d, k, n, H=H).tocsr() for d in range(1, 2 * D + 1)]
+    steprule, v_point = no.vlasov_steprule(D, k, n, Ds, m2n.tocsr(), n2p.tocsr(), p2n.tocsr(), n2m.tocsr(), F_point)
+    plan = gsg.Plan(2 * D, k, n, "sparse", H=_scipy(H))
+    return dict(D=D, k=k, n=n, mats=(m2n, n2p, p2n, n2m), F=F_point, f0=f0, steprule=steprule, v_point=v_point, plan=plan)
+
+
+def test_vlasov_steprule(gsg, vlasov_setup):
+    """steprule(t, f) on the device against the oracle's restatement with the same matrices and F_point."""
+    s = vlasov_setup
+    rhs = gsg.VlasovRHS(s["plan"], *s["mats"], s["F"])
+    for i in range(s["D"]):
+        assert relerr(rhs.v_point(i), s["v_point"][i]) <= TOL
+    for f in (s["f0"], random_state(s["plan"].size, seed=21)):
+        ref = s["steprule"](0.0, f)
+        err = relerr(rhs(0.0, f), ref)
+        print(f"vlasov steprule (4-D, k=3, n=3): {err:.3e}")
+        assert err <= TOL
+    with pytest.raises(ValueError):
+        gsg.VlasovRHS(s["plan"], *s["mats"], s["F"][:1])
+    rhs.close()
+
+
+@pytest.mark.parametrize("order", ["45", "78"])
+def test_vlasov_evolve_specified_points(gsg, vlasov_setup, order, tmp_path, monkeypatch):
+    """vlasov_evolve(D, k, n, m2n, n2p, p2n, n2m, f0, F_point, t0, t1, nout; order, points=:specified) against the
+    restated ODE.jl on the oracle's steprule; the dump keeps the reference's dataset names."""
+    import ode_oracle as oo
+    s = vlasov_setup
+    D, k, n = s["D"], s["k"], s["n"]
+    monkeypatch.setitem(gsg._PLANS, (2 * D, k, n, "sparse"), s["plan"])
+    t0, t1, nout = 0.0, 0.02, 3
+    tspan = np.linspace(t0, t1, nout)
+    st = {}
+    t_ref, y_ref = oo.oderk_adapt(s["steprule"], s["f0"], tspan, oo.TABLEAUS[order], points="specified", stats=st)
+    dump = str(tmp_path / "vlasov.npz")
+    tout, yout = gsg.vlasov_evolve(D, k, n, *s["mats"], s["f0"], s["F"], t0, t1, nout, order=order, points="specified", dump=dump)
+    assert list(tout) == list(t_ref)
+    worst = max(relerr(a, b) for a, b in zip(yout, y_ref))
+    print(f"vlasov_evolve ode{order}: {st}, worst output vs oracle {worst:.3e}")
+    assert worst <= 1e-11
+    assert relerr(yout[-1], s["f0"]) > 1e-4                     # the distribution moved
+    meta, ops, times, states = gsg.read_dump(dump)
+    assert meta == {"dimensions": D, "order": k, "levels": n} and set(ops) == {"m2n", "n2p", "p2n", "n2m"}
+    assert len(states) == nout and np.array_equal(states[-1], yout[-1])

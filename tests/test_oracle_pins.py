@@ -309,3 +309,35 @@ def test_ode_reference_solver_assertions(oracle):
         E = [sum(np.sum((A @ y[:N]) ** 2) for A in mats) + np.sum(y[N:] ** 2) for y in yout]
         assert 0 < E[0] - E[-1] < 1.0e-8, (order, E[0] - E[-1])
         assert all(abs(math.sqrt(e) - math.sqrt(2) * math.pi) < 1.0e-4 for e in E)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# nodal / point transforms (oracle/nodal_oracle.py): the reference's own assertions, test/transformations.jl:15-79
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_transform_1D_mutual_inverses(k):
+    import nodal_oracle as no
+    n = 5
+    I = np.eye(k << n)
+    for a, b in (("points", "nodal"), ("points", "modal"), ("nodal", "modal"), ("pos", "modal")):
+        A, B = no.transform_1D(k, n, a, b), no.transform_1D(k, n, b, a)
+        assert np.linalg.norm(A @ B - I) < 1e-15 * 10 ** k, (k, a, b)
+        assert np.linalg.norm(B @ A - I) < 1e-15 * 10 ** k, (k, a, b)
+
+
+def test_transform_2D_mutual_inverses_and_literal_loop():
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    import nodal_oracle as no
+    D, k, n = 2, 3, 5
+    I = sp.identity(3072 if False else no.o.get_size(D, k, n))
+    for a, b in (("points", "nodal"), ("nodal", "modal")):
+        A = no.transform(D, k, n, no.transform_1D(k, n, a, b))
+        B = no.transform(D, k, n, no.transform_1D(k, n, b, a))
+        assert spl.norm(A @ B - I) < 1e-10 and spl.norm(B @ A - I) < 1e-10
+    # block-Kronecker assembly == the reference's scalar column loop (make_column / inner_loop), entry for entry
+    for a, b in (("modal", "nodal"), ("nodal", "points")):
+        m1 = no.transform_1D(3, 2, a, b)
+        A, B = no.transform(2, 3, 2, m1), no.transform_literal(2, 3, 2, m1)
+        assert A.nnz == B.nnz and abs(A - B).max() == 0.0

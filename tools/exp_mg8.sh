@@ -8,8 +8,6 @@ PY
 }
 run n8 8 A=1
 run n8_rs8 8 GSG_LONG_RSPLIT=8
-run n8_onestream 8 GSG_RHS_ONE_STREAM=1
-run n8_serial 8 GSG_RHS_SERIAL=1
+run n8_nozero 8 GSG_MG_NO_ZERO=1
 run n4 4 A=1
-run n4_rs8 4 GSG_LONG_RSPLIT=8
 run n2 2 A=1

@@ -30,7 +30,9 @@ CONFIGS = {
     "d6k3n8": (6, 3, 8),     # config 4, the one the metric is quoted on (fits one B200: 276 MB state)
     "d4k3n7": (4, 3, 7),     # config 3 operator (latency regime)
     "d2k3n8": (2, 3, 8),     # config 2 operator (latency regime)
+    "recon": (4, 4, 8),      # config 5: reconstruct_DG of a D=4 sparse k=4 n=8 interpolant (points/s)
 }
+FP64_PEAK_TFLOPS = 37.0      # nominal B200 fp64 (MEASURED_PEAKS.json holds only the copy bandwidth and the bf16 GEMM)
 DT = 1.0e-4                  # stable for RK4 at D=6, n=8 (dt_max ~ 2.2e-4)
 
 
@@ -247,6 +249,113 @@ def workload_name(D, k, n, N):
             f"(BASELINE config {4 if (D, k, n) == (6, 3, 8) else '-'})")
 
 
+def run_recon(args, rank, local_rank, world):
+    """--config recon: batched reconstruct_DG (BASELINE config 5).  One step = one batch of `npts` uniform points
+    (counter-based generator, seed 20240); points are sharded over the ranks, coefficients replicated."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gsg_b200 as g
+    D, k, n = CONFIGS["recon"]
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    npts_total = int(float(os.environ.get("GSG_RECON_NPTS", "2e7")))
+    npts = npts_total // world
+    W, K = max(args.warmup, 3), args.steps
+    plan = g.Plan(D, k, n, device=local_rank)
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    plan.set_stream(stream)
+    v1 = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
+    coef = plan.tensor_construct_dev([v1] * D, device=device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(20240 + rank)
+    pts = torch.rand(npts, D, dtype=torch.float64, device=device, generator=gen)
+    out = torch.empty(npts, dtype=torch.float64, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(W):
+        plan.reconstruct_dev(coef, pts, npts, out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    l0 = g.launch_count()
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        plan.reconstruct_dev(coef, pts, npts, out)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = g.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = npts * world * K / (ms * 1e-3)
+    exact = torch.prod(torch.sin(2 * math.pi * pts), dim=1)
+    rms = float(torch.sqrt(torch.mean((out - exact) ** 2)))
+    # e2e: host points in, host values out, through the host-pointer entry point
+    hp = pts[: min(npts, 4_000_000)].cpu().pin_memory()
+    hv = g.tensor_construct(D, k, n, [v1] * D)
+    plan.reconstruct(hv, hp.numpy()[:1000])
+    barrier()
+    t0 = time.perf_counter()
+    vals = plan.reconstruct(hv, hp.numpy())
+    t1 = time.perf_counter()
+    e2e_rate = hp.shape[0] / (t1 - t0)
+    if world > 1:
+        tt = torch.tensor([e2e_rate], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        e2e_rate = float(tt.item())
+    nlev = math.comb(n + D, D)
+    flop_pt = 2.0 * nlev * sum(k ** j for j in range(1, D + 1))            # SURVEY 8d: separable contraction
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gsg_oracle as o
+        sample = hp.numpy()[:1024]
+        o.reconstruct_DG_batch(D, k, n, hv, sample[:8])
+        tc0 = time.perf_counter()
+        ref = o.reconstruct_DG_batch(D, k, n, hv, sample)
+        tc1 = time.perf_counter()
+        cb = {"value": sample.shape[0] / (tc1 - tc0), "unit": "points/s", "cores": 1, "kind": "port",
+              "sample": f"oracle.reconstruct_DG_batch (numpy restatement of src/dg_methods.jl:150-165) on the first "
+                        f"{sample.shape[0]} points", "max_abs_diff_vs_gpu": float(np.abs(ref - vals[:sample.shape[0]]).max())}
+    if rank == 0:
+        line = {
+            "metric": "reconstruct_DG points/sec (D=%d sparse, k=%d, n=%d)" % (D, k, n), "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"reconstruct_DG batch, D={D} sparse k={k} n={n} interpolant of prod sin(2 pi x_d), "
+                                   f"{npts * world} uniform points per step (BASELINE config 5 evaluates 1e8; GSG_RECON_NPTS sets it)",
+                       "l2": "coefficients (21.5 MB) are L2-resident by design; points stream from HBM (40 B per point)",
+                       "parallelism": "single GPU" if world == 1 else f"points sharded over {world} GPUs, coefficients replicated"},
+            "roofline": {"bound": "fp64", "kernel": "reconstruct3_kernel", "achieved": value * flop_pt / 1e12,
+                         "peak": FP64_PEAK_TFLOPS * world, "unit": "TFLOP/s", "frac": value * flop_pt / 1e12 / (FP64_PEAK_TFLOPS * world),
+                         "traffic": None, "peak_source": "nominal B200 fp64 FMA rate (no measured fp64 peak in MEASURED_PEAKS.json)",
+                         "flop_per_point": flop_pt,
+                         "note": "flops = 2 |Lambda| sum_{j<=D} k^j per point (separable contraction, SURVEY 8d); the timed step "
+                                 "includes the Morton-key radix sort of the points (cub) and the contraction kernel"},
+            "cpu_baseline": cb,
+            "e2e": {"value": e2e_rate, "unit": "points/s", "h2d_bytes_per_step": 8.0 * D * hp.shape[0], "d2h_bytes_per_step": 8.0 * hp.shape[0],
+                    "call": f"gsg_reconstruct(plan, vcoeffs_host, points_host[{hp.shape[0]}], out_host): coefficients + points H2D, kernel, values D2H"},
+            "gpu_launches": int(launches), "clocks": clocks, "rms_error_vs_exact": rms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -261,6 +370,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.config == "recon":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the RK4 path; --config recon carries its own cpu_baseline"}))
+            return
+        run_recon(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, D, k, n, rank, world)
         return
@@ -283,11 +398,12 @@ def main():
 
     plan = g.Plan(D, k, n, device=local_rank)
     N = plan.size
-    u0 = synthetic_state(g, D, k, n)
+    v1d = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
+    u0 = g.tensor_construct(D, k, n, [v1d] * D)                  # host copy for the end-to-end (host buffer) leg
     stream = torch.cuda.Stream(device=device)
     torch.cuda.set_stream(stream)
     plan.set_stream(stream)
-    y = plan.to_device(u0, device=device)
+    y = plan.tensor_construct_dev([v1d] * D, device=device)      # initial data expanded on the device (gsg_tensor_construct_dev)
 
     def barrier():
         if world > 1:
@@ -383,9 +499,14 @@ def main():
                      "short-pole groups; algorithmic = 16 B per DOF per directional apply (SURVEY 8d), so a PAIR "
                      "launch counts 32 B/DOF while moving 16-24; 'traffic' = ncu DRAM bytes per launch averaged over "
                      "one RHS; timed: the first launches of the timed region (bounded sample)"),
+            # whole-step effective bandwidth under three byte models: SURVEY 8(d)'s contract model
+            # (4 x 16 D + 144 B/DOF: staged stage updates), what the timed Taylor form needs by the same accounting
+            # (4 x 16 D + 48), and the staged form measured beside it (filled in below)
             "step_model": {"bytes_per_dof_model": 64 * D + 144,
                            "achieved_gbs": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9,
-                           "frac": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9 / peak},
+                           "frac": (64 * D + 144) * N * K / (ms * 1e-3) / 1e9 / peak,
+                           "taylor": {"bytes_per_dof": 64 * D + 48,
+                                      "frac": (64 * D + 48) * N * K / (ms * 1e-3) / 1e9 / peak}},
         }
 
     # ---- e2e: the C-ABI evolve call on HOST buffers (H2D + K steps + D2H inside the timed region)
@@ -459,6 +580,9 @@ def main():
         staged_ms = s0.elapsed_time(s1) / ks
         plan.set_rk4_mode(0)
 
+    if roofline is not None and staged_ms:
+        roofline["step_model"]["staged"] = {"bytes_per_dof": 64 * D + 144, "ms_per_step": staged_ms,
+                                            "frac": (64 * D + 144) * N / (staged_ms * 1e-3) / 1e9 / peak}
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(D, k, n)

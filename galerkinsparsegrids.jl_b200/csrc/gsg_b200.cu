@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <nvtx3/nvToolsExt.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -182,6 +183,8 @@ struct gsg_plan {
     // workspaces (device layout)
     DevBuf<double> wx, wy, wk, wacc, ww, wtmp, wred;
     DevBuf<double> wpts, wout;
+    DevBuf<unsigned> rkeys, rkeys2, rperm, rperm2;     // reconstruct: Morton keys / permutation (sorted points)
+    DevBuf<unsigned char> rtemp;
     DevBuf<int> tile_counter;     // dynamic tile schedulers of the persistent kernels: one slot per launch, round robin
     int ctr_next = 0;
     // concurrent right-hand side (rhs_concurrent): pool of high-priority streams for the long-pole launches of ALL
@@ -2136,9 +2139,48 @@ int gsg_reconstruct_dev(gsg_plan* plan, const double* vcoeffs_dev, const double*
     T.KD = (int)pl.S.kD;
     T.KDp = (int)pl.S.kDp;
     T.legw = 2 * (gsg::K_MAX + 1);
+    // third-generation kernel (k <= 5, D <= 4): Morton-sorted points, one thread per 2 points, separable contraction
+    if (T.k >= 2 && T.k <= 5 && T.D >= 1 && T.D <= 4 && npts >= 64 && npts < (1LL << 31) && !getenv("GSG_RECON_V2")) {
+        nvtx_range nvtx_r("reconstruct (sorted, separable)");
+        const int bits = std::min(10, 32 / T.D);
+        GSG_TRY(pl.rkeys.resize((size_t)npts)); GSG_TRY(pl.rkeys2.resize((size_t)npts));
+        GSG_TRY(pl.rperm.resize((size_t)npts)); GSG_TRY(pl.rperm2.resize((size_t)npts));
+        recon_keys_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, pl.stream>>>(points_dev, npts, T.D, bits, pl.rkeys.p, pl.rperm.p);
+        size_t tbytes = 0;
+        GSG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tbytes, pl.rkeys.p, pl.rkeys2.p, pl.rperm.p, pl.rperm2.p, (int)npts, 0,
+                                                 bits * T.D, pl.stream));
+        GSG_TRY(pl.rtemp.resize(tbytes + 16));
+        GSG_CUDA(cub::DeviceRadixSort::SortPairs(pl.rtemp.p, tbytes, pl.rkeys.p, pl.rkeys2.p, pl.rperm.p, pl.rperm2.p, (int)npts, 0,
+                                                 bits * T.D, pl.stream));
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        constexpr int C = 2;
+        const unsigned grid3 = (unsigned)((npts + 128 * C - 1) / (128 * C));
+        const auto& L = gsg::leg_coeffs();
+        const auto& G = gsg::dg_coeffs(T.k);
+        int rc3 = -1;
+        auto launch3 = [&](auto kc, auto dc) -> int {
+            constexpr int K = decltype(kc)::value, DD = decltype(dc)::value;
+            ReconBasis<K> Bs;
+            for (int m = 0; m < K; ++m) {
+                for (int i = 0; i < K; ++i) Bs.leg[m][i] = L[m][i];
+                for (int i = 0; i < 2 * K; ++i) Bs.dg[m][i] = G[m][i];
+            }
+            reconstruct3_kernel<K, DD, C><<<grid3, 128, 0, pl.stream>>>(T, Bs, vcoeffs_dev, points_dev, pl.rperm2.p, npts, out_dev);
+            return 0;
+        };
+#define GSG_R3(KK, DD) if (T.k == KK && T.D == DD) rc3 = launch3(std::integral_constant<int, KK>{}, std::integral_constant<int, DD>{});
+        GSG_R3(2, 1) GSG_R3(2, 2) GSG_R3(2, 3) GSG_R3(2, 4) GSG_R3(3, 1) GSG_R3(3, 2) GSG_R3(3, 3) GSG_R3(3, 4)
+        GSG_R3(4, 1) GSG_R3(4, 2) GSG_R3(4, 3) GSG_R3(4, 4) GSG_R3(5, 1) GSG_R3(5, 2) GSG_R3(5, 3) GSG_R3(5, 4)
+#undef GSG_R3
+        if (rc3 == 0) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            GSG_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const int nwarp = 8;
     // second-generation kernel: factored mode products (low / high half of the dimensions)
-    if (!getenv("GSG_RECON_V1")) {
+    {
         const int nlow = (T.D + 1) / 2;
         long long KL = 1, KH = 1;
         for (int d = 0; d < nlow; ++d) KL *= T.k;

@@ -1609,6 +1609,201 @@ reconstruct2_kernel(ReconTables T, const double* __restrict__ coeffs, const doub
 }
 
 // ------------------------------------------------------------------------------------------
+// Third-generation reconstruct kernel (round 2; the shipped path for k <= 5, D <= 4): one THREAD per C points.
+// The warp-per-point kernels above re-read the k^D coefficients of every multi-level for every point through
+// L1/L2 (~1 MB per point at D=4, k=4, n=8) and spend their instructions on index arithmetic.  Here
+//   * the points are sorted by a Morton key of their leading bits first (host side, cub radix sort), so the C
+//     points of a thread and the 32 threads of a warp fall into the same cell of almost every multi-level: a
+//     coefficient is loaded ONCE per thread (one L1 sector per warp) and used for C points;
+//   * the sum over the k^D modes is evaluated as the SEPARABLE contraction
+//         sum_{m_D} v_D[m_D] ( ... sum_{m_2} v_2[m_2] ( sum_{m_1} v_1[m_1] c[m_1, m_2, .., m_D] ) ... )
+//     in memory order: k^D + k^(D-1) + ... + k FMAs and D accumulators instead of D multiplications per mode;
+//   * the D*k one-dimensional basis values of a point live in registers and are re-evaluated only for the
+//     dimensions whose level changed between consecutive multi-levels (the layout order changes dimension 1
+//     fastest); the basis coefficient tables are kernel parameters (constant-bank operands).
+// Basis values follow `v` / `array2poly` op for op (un-contracted Horner, src/1d_dg_functions.jl:15-28).
+// ------------------------------------------------------------------------------------------
+template <int K>
+struct ReconBasis {                // leg[m][i], dg[m][i] for i < K (lower half) and the sgn-part dg[m][K + i]
+    double leg[K][K];
+    double dg[K][2 * K];
+};
+
+template <int K, int C, int DIM>
+struct ReconContract {
+    // res[c] = contraction of the sub-block at cf (dimensions 0..DIM) with the basis values of point c
+    template <int NV>
+    static __device__ __forceinline__ void run(const double* const (&cf)[NV], const double (&v)[C][4][K], double (&res)[C]) {
+        constexpr int STRIDE = DIM == 0 ? 1 : (DIM == 1 ? K : (DIM == 2 ? K * K : K * K * K));
+#pragma unroll
+        for (int c = 0; c < C; ++c) res[c] = 0.0;
+        if constexpr (DIM == 0 && NV == 1 && (K % 2) == 0) {
+            // k even: every row of k coefficients starts 16-byte aligned (cells are padded to an even length)
+#pragma unroll
+            for (int m = 0; m < K; m += 2) {
+                const double2 cv = __ldg(reinterpret_cast<const double2*>(cf[0] + m));
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    res[c] = fma(cv.x, v[c][0][m], res[c]);
+                    res[c] = fma(cv.y, v[c][0][m + 1], res[c]);
+                }
+            }
+        } else if constexpr (DIM == 0) {
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                if constexpr (NV == 1) {
+                    const double cv = __ldg(cf[0] + m);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) res[c] = fma(cv, v[c][0][m], res[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) res[c] = fma(__ldg(cf[c] + m), v[c][0][m], res[c]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const double* sub[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) sub[i] = cf[i] + m * STRIDE;
+                double r[C];
+                ReconContract<K, C, DIM - 1>::template run<NV>(sub, v, r);
+#pragma unroll
+                for (int c = 0; c < C; ++c) res[c] = fma(r[c], v[c][DIM][m], res[c]);
+            }
+        }
+    }
+};
+
+template <int K>
+__device__ __forceinline__ double recon_poly(const double* __restrict__ lo, const double* __restrict__ hi, double x) {
+    // array2poly restricted to the K coefficients that can be non-zero (the skipped leading terms are exact zeros)
+    if (fabs(x) > 1.0) return 0.0;
+    const bool neg = signbit(x);
+    double s = 0.0;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+        const double t = hi ? (neg ? -hi[i] : hi[i]) : 0.0;
+        s = __dadd_rn(__dmul_rn(s, x), lo[i] + t);
+    }
+    return s;
+}
+
+#ifndef GSG_RECON3_MINB
+#define GSG_RECON3_MINB 3
+#endif
+template <int K, int D, int C>
+__global__ void __launch_bounds__(128, GSG_RECON3_MINB)
+reconstruct3_kernel(ReconTables T, const __grid_constant__ ReconBasis<K> B, const double* __restrict__ coeffs,
+                    const double* __restrict__ pts, const unsigned* __restrict__ perm, long long npts,
+                    double* __restrict__ out) {
+    static_assert(D >= 1 && D <= 4, "instantiated for D <= 4");
+    const long long t0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * C;
+    if (t0 >= npts) return;
+    const double sqrt2 = sqrt(2.0);
+    long long idx[C];
+    double x[C][D];
+    bool bad[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const long long i = t0 + c < npts ? t0 + c : npts - 1;          // tail: recompute the last point
+        idx[c] = perm[i];
+        bad[c] = false;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            x[c][d] = pts[idx[c] * D + d];
+            bad[c] = bad[c] || !(x[c][d] >= 0.0 && x[c][d] <= 1.0);      // BoundsError in the reference: flag, never index
+            if (bad[c]) x[c][d] = 0.0;
+        }
+    }
+    double v[C][4][K];
+    int cell[C][D];
+    int lprev[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) lprev[d] = -1;
+    double acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.0;
+
+    for (int b = 0; b < T.nblocks; ++b) {
+        const unsigned char* lv = T.blk_level + (size_t)b * D;
+        int l[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) l[d] = lv[d];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (l[d] == lprev[d]) continue;
+            lprev[d] = l[d];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double xd = x[c][d];
+                long long cl;                                            // 1-based, src/dg_methods.jl:70-79
+                if (l[d] <= 1) cl = 1;
+                else if (xd >= 1.0) cl = 1LL << (l[d] - 1);
+                else cl = 1 + (long long)floor((double)(1LL << (l[d] - 1)) * xd);
+                cell[c][d] = (int)(cl - 1);
+                if (l[d] == 0) {
+                    const double y = 2.0 * xd - 1.0;
+#pragma unroll
+                    for (int m = 0; m < K; ++m) v[c][d][m] = recon_poly<K>(B.leg[m], nullptr, y) * sqrt2;
+                } else {
+                    const double sc = (double)(1LL << l[d]);
+                    const double y = sc * xd - (double)(2 * cl - 1);
+                    const double sq = sqrt(sc);
+#pragma unroll
+                    for (int m = 0; m < K; ++m) v[c][d][m] = recon_poly<K>(B.dg[m], B.dg[m] + K, y) * sq;
+                }
+            }
+        }
+        const long long boff = T.blk_offset[b];
+        const double* cf[C];
+        bool same = true;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            long long lin = 0, stride = 1;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                lin += (long long)cell[c][d] * stride;
+                stride *= (l[d] <= 1) ? 1 : (1LL << (l[d] - 1));
+            }
+            cf[c] = coeffs + boff + lin * T.KDp;
+            same = same && cf[c] == cf[0];
+        }
+        double r[C];
+        if (same) {
+            const double* const one[1] = {cf[0]};
+            ReconContract<K, C, D - 1>::template run<1>(one, v, r);
+        } else {
+            const double* many[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) many[c] = cf[c];
+            ReconContract<K, C, D - 1>::template run<C>(many, v, r);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += r[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if (t0 + c < npts) out[idx[c]] = bad[c] ? __longlong_as_double(0x7ff8000000000000LL) : acc[c];
+}
+
+// Morton key of the leading `bits` bits of every coordinate (dimension 0 in the least significant position)
+__global__ void recon_keys_kernel(const double* __restrict__ pts, long long npts, int D, int bits, unsigned* __restrict__ keys,
+                                  unsigned* __restrict__ vals) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    unsigned key = 0;
+    const double scale = (double)(1u << bits);
+    for (int d = 0; d < D; ++d) {
+        const double xd = pts[i * D + d];
+        unsigned q = (xd >= 0.0 && xd < 1.0) ? (unsigned)(xd * scale) : (xd >= 1.0 ? (1u << bits) - 1u : 0u);
+        for (int bb = 0; bb < bits; ++bb) key |= ((q >> bb) & 1u) << (bb * D + d);
+    }
+    keys[i] = key;
+    vals[i] = (unsigned)i;
+}
+
+// ------------------------------------------------------------------------------------------
 // CSR SpMV cross-check: LANES lanes per row, int32 columns.
 // ------------------------------------------------------------------------------------------
 template <int LANES>

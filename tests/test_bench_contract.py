@@ -1,5 +1,5 @@
 """The reference arm of bench.py runs without a GPU: check the JSON line contract here (the GPU arm's line has the
-same keys plus roofline / clocks and is produced on the B200 box; profiles/r1_bench_n1.json holds the last one)."""
+same keys plus roofline / clocks and is produced on the B200 box; profiles/r2_bench_n1.json holds the last one)."""
 import json
 import os
 import subprocess
@@ -21,7 +21,7 @@ def test_reference_arm_json_line():
 
 
 def test_committed_gpu_bench_line_has_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
@@ -31,3 +31,17 @@ def test_committed_gpu_bench_line_has_contract_keys():
     assert r["bound"] == "hbm" and 0 < r["frac"] < 1.5 and r["unit"] == "GB/s"
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    sm = r["step_model"]
+    assert sm["bytes_per_dof_model"] == 528 and sm["taylor"]["bytes_per_dof"] == 432 and sm["staged"]["ms_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and "COMPLETE" in line["cpu_baseline"]["sample"]
+
+
+def test_committed_multi_gpu_and_recon_lines():
+    for n in (2, 4, 8):
+        with open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")) as f:
+            line = json.loads(f.read().strip().splitlines()[-1])
+        assert line["n_gpus"] == n and line["scaling"] == "strong" and line["gpu_launches"] > 0
+        assert "gsg_mg" in line["config"]["parallelism"] and line["e2e"]["value"] > 0
+    with open(os.path.join(ROOT, "profiles", "r2_bench_recon.json")) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    assert line["unit"] == "points/s" and line["roofline"]["bound"] == "fp64" and line["cpu_baseline"]["max_abs_diff_vs_gpu"] < 1e-12

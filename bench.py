@@ -488,13 +488,18 @@ def main():
                 traffic = json.load(open(tpath)).get("sweep_stream_kernel_bytes_per_launch")
             except Exception:
                 traffic = None
+        flat = plan.flat_active
         roofline = {
-            "bound": "hbm", "kernel": "sweep_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "bound": "hbm", "kernel": "sweep_flat_kernel" if flat else "sweep_stream_kernel", "achieved": achieved,
+            "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None if flat else traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_ms, "timed_launches": n_prof,
-            # per step: 4 RHS x (D/2 PAIR launches + D reduced launches) of this kernel family
-            "kernel_share_of_step": (prof_ms / n_prof) * (4 * (D + D // 2)) / (ms / K),
-            "note": ("sweep_stream_kernel<K, PAIR> family: per RHS D/2 direction-pair launches (2-D sub-planes with "
+            # per step: 4 RHS x (D/2 PAIR launches + D reduced launches) of the streaming family; flat: 4 launches
+            "kernel_share_of_step": (prof_ms / n_prof) * (4 if flat else 4 * (D + D // 2)) / (ms / K),
+            "note": ("sweep_flat_kernel: ONE launch per right-hand side covers every direction (small index sets: the "
+                     "state sits in L2, a step is launch-latency bound, so the HBM roofline fraction is not the figure of "
+                     "merit here -- ms_per_step is); algorithmic = 16 B per DOF per directional apply" if flat else
+                     "sweep_stream_kernel<K, PAIR> family: per RHS D/2 direction-pair launches (2-D sub-planes with "
                      "n' <= 2, two directional applies from one load / one store) + D launches over the remaining "
                      "short-pole groups; algorithmic = 16 B per DOF per directional apply (SURVEY 8d), so a PAIR "
                      "launch counts 32 B/DOF while moving 16-24; 'traffic' = ncu DRAM bytes per launch averaged over "
@@ -596,7 +601,9 @@ def main():
             "config": {"workload": workload_name(D, k, n, N),
                        "rk4_form": "Taylor form for the linear RHS: 4 operator applies + 1 combine pass (staged form timed beside it)",
                        "initial_condition": "prod_d sin(2 pi x_d) via tensor_construct", "dt": DT,
-                       "l2": "inputs larger than L2 (4 state-sized vectors x %.0f MB vs 126 MB L2)" % (8e-6 * N),
+                       "l2": ("inputs larger than L2 (4 state-sized vectors x %.0f MB vs 126 MB L2)" % (8e-6 * N) if 40e-6 * N > 126 else
+                              "state smaller than L2 (%.2f MB): latency regime, no flush between steps (a flush would time the flush)" % (8e-6 * N)),
+                       "sweep_path": "flat kernel (one launch per right-hand side)" if plan.flat_active else "tiled class kernels",
                        "parallelism": ("single GPU" if world == 1 else
                                        f"multi-level blocks partitioned over {world} GPUs by level==0 of the last "
                                        f"{world.bit_length() - 1} dimension(s); per RHS 2 point-to-point messages per "

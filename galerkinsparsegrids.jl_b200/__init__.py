@@ -74,6 +74,18 @@ def block_pattern(n: int) -> np.ndarray:
     return out.astype(bool)
 
 
+def flat_tables(D: int, k: int, n: int, d: int, scheme: str = "sparse"):
+    """CPU-side copy of the flat kernel's tables for direction d (1-based): (groups [ngroups, 20] int64 =
+    {base[0..16], p, S, nitems}, cells [ncells, 3] int32 = {group, item, 1-D cell})."""
+    ng, ncell = C.c_int64(0), C.c_int64(0)
+    check(lib.gsg_debug_flat_tables(D, k, n, _scheme(scheme), d, None, None, C.byref(ng), C.byref(ncell)))
+    groups = np.zeros((ng.value, 20), dtype=np.int64)
+    cells = np.zeros((ncell.value, 3), dtype=np.int32)
+    check(lib.gsg_debug_flat_tables(D, k, n, _scheme(scheme), d, groups.ctypes.data_as(C.c_void_p),
+                                    cells.ctypes.data_as(C.c_void_p), C.byref(ng), C.byref(ncell)))
+    return groups, cells
+
+
 def get_size(D: int, k: int, n: int, scheme: str = "sparse") -> int:
     """get_size(Val(D), k, n, Val(scheme)) -- src/dg_vmethods.jl:35-45."""
     out = C.c_int64()
@@ -330,6 +342,16 @@ class Plan:
     def set_rk4_mode(self, mode: int) -> None:
         """0 = automatic (Taylor form for the linear right-hand sides), 1 = always the staged form."""
         check(lib.gsg_plan_set_rk4_mode(self._h, int(mode)))
+
+    def set_flat(self, mode: int) -> None:
+        """0 = tiled class kernels, 1 = flat kernel (one launch per right-hand side), 2 = automatic (default)."""
+        check(lib.gsg_plan_set_flat(self._h, int(mode)))
+
+    @property
+    def flat_active(self) -> bool:
+        out = C.c_int(0)
+        check(lib.gsg_plan_flat_active(self._h, C.byref(out)))
+        return bool(out.value)
 
     def set_partition(self, rank: int, nranks: int) -> None:
         """Block partition over nranks = 2^b ranks (include/gsg_b200.h): afterwards the plan's sweeps

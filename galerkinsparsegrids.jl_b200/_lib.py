@@ -73,6 +73,9 @@ SIGNATURES = {
     "gsg_plan_partition_blocks": (i32, [vp, i32, i32, vp, vp, p_i64, C.POINTER(i32)]),
     "gsg_rk4_taylor_cells_dev": (i32, [vp, vp, i64, vp, vp, vp, vp, vp, f64, f64, f64, f64]),
     "gsg_plan_set_rk4_mode": (i32, [vp, i32]),
+    "gsg_plan_set_flat": (i32, [vp, i32]),
+    "gsg_plan_flat_active": (i32, [vp, C.POINTER(i32)]),
+    "gsg_debug_flat_tables": (i32, [i32, i32, i32, i32, i32, vp, vp, p_i64, p_i64]),
     "gsg_ode_create": (i32, [vp, i32, vp, vp, i32, f64, f64, vp, f64, f64, C.POINTER(vp)]),
     "gsg_ode_destroy": (i32, [vp]),
     "gsg_ode_step": (i32, [vp, p_f64, p_f64, C.POINTER(i32)]),

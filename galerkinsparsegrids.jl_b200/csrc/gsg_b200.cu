@@ -125,6 +125,7 @@ struct SweepClass {          // one launch of a sweep
 struct Direction {
     int A = 1;               // K^(d-1)
     DevBuf<GroupDev> groups;
+    std::vector<GroupDev> groups_h;
     DevBuf<CellOfs> celltab;     // register-tiled long kernel: per group, one entry per 1-D cell
     DevBuf<int> offtab;          // in-cell offset of pole j: a + K*A*b
     std::vector<SweepClass> classes;
@@ -194,6 +195,20 @@ struct gsg_plan {
     cudaEvent_t ev_p1 = nullptr;
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
+
+    // flat path (kernels.cuh, sweep_flat_kernel): one launch per right-hand side for small index sets.
+    // flat_mode: 0 = never, 1 = whenever supported, 2 = automatic (N * D <= FLAT_AUTO_MAX)
+    int flat_mode = 2;
+    DevBuf<FlatCell> flat_cells;
+    // pre-squared Laplacian blocks S_p = (H[0:N',0:N'])^2 of the short classes p <= sq_pmax (dense there anyway;
+    // for the long classes the square is completely dense -- level 0 touches every cell -- so those stay D(D x))
+    int sq_pmax = -1;
+    std::vector<double> dense_sq_host;                     // same layout as dense_host
+    DevBuf<int> sq_rowptr, sq_col;
+    DevBuf<double> sq_val;
+    int sq_cls_row0[MAXL + 1] = {0};
+    bool use_sq = false;        // the streaming launches take the squared dense blocks (set by laplacian())
+    int kind_filter = 0;        // 0 = every class, 1 = streaming classes only, 2 = long classes only
 
     // RK4 driver: 0 = automatic (linear right-hand sides use the Taylor form), 1 = always staged
     int rk4_mode = 0;
@@ -326,6 +341,39 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         if (all.size() < want) all.resize(want, 0.0);
     }
     P.dense_host = all;
+
+    // pre-squared blocks of the short classes: (D_op * D_op) restricted to a pole is the square of the pole's
+    // principal sub-block (poles are closed under D_op), summed over the inner index in ascending order as
+    // SparseArrays' A*B does (src/multidim_derivative.jl:76); no FMA contraction (host_setup.cpp)
+    P.sq_pmax = P.short_pmax;
+    P.dense_sq_host.assign(all.size(), 0.0);
+    {
+        std::vector<int> rp, cl;
+        std::vector<double> vl;
+        for (int p = 0; p <= P.sq_pmax; ++p) {
+            const int NP = K << p, nq = 1 << p;
+            std::vector<double> a((size_t)NP * NP), sq((size_t)NP * NP);
+            for (int i = 0; i < NP; ++i)
+                for (int j = 0; j < NP; ++j) a[(size_t)i * NP + j] = Hd[(size_t)i * N1 + j];
+            gsg::dense_square(a.data(), NP, sq.data());
+            std::copy(sq.begin(), sq.end(), P.dense_sq_host.begin() + P.hoff[p]);
+            P.sq_cls_row0[p] = (int)rp.size();
+            for (int q = 0; q < nq; ++q) {
+                rp.push_back((int)cl.size());
+                for (int qc = 0; qc < nq; ++qc) {
+                    cl.push_back(qc);
+                    const size_t o = vl.size();
+                    vl.resize(o + P.KK2, 0.0);
+                    for (int mo = 0; mo < K; ++mo)
+                        for (int mi = 0; mi < K; ++mi) vl[o + mo * K + mi] = sq[(size_t)(q * K + mo) * NP + (qc * K + mi)];
+                }
+            }
+            rp.push_back((int)cl.size());
+        }
+        GSG_TRY(P.sq_rowptr.upload(rp));
+        GSG_TRY(P.sq_col.upload(cl));
+        GSG_TRY(P.sq_val.upload(vl));
+    }
     return 0;
 }
 
@@ -374,15 +422,11 @@ int get_col_passes(gsg_plan& P, int p, int npass, const std::vector<std::unique_
     return 0;
 }
 
-int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_np /* -1: keep every group */) {
-    const gsg::IndexSet& S = P.S;
-    const int D = S.D, K = S.k, n = S.n;
-    dir.A = pow_int(K, d);
-    const int KD = (int)S.kD, KDp = (int)S.kDp;
-    const int PI = KD / K;
-
-    // groups keyed by the other dims' levels, in layout order of their level_d = 0 block
-    std::vector<GroupDev> groups;
+// pole groups of direction d (0-based), keyed by the other dims' levels, in layout order of their level_d = 0 block.
+// Pure host code (also used by the CPU-side table checks, gsg_debug_flat_tables).
+int host_groups(const gsg::IndexSet& S, int d, int part_rank, int part_bits, int exclude_np, std::vector<GroupDev>& groups) {
+    const int D = S.D, n = S.n;
+    groups.clear();
     for (const gsg::Block& b0 : S.blocks) {
         if (b0.level[d] != 0) continue;
         GroupDev g;
@@ -407,9 +451,9 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         // with p >= 1 straddles the pair of ranks that differ in that bit; the rank holding level >= 1
         // (bit 0) sweeps it after receiving the level-0 cells, p == 0 poles stay with the bit-1 rank.
         bool mine = true;
-        for (int j = 0; j < P.part_bits; ++j) {
+        for (int j = 0; j < part_bits; ++j) {
             const int e = D - 1 - j;
-            const int mybit = (P.part_rank >> j) & 1;
+            const int mybit = (part_rank >> j) & 1;
             if (e == d) mine = mine && (g.p == 0 ? mybit == 1 : mybit == 0);
             else mine = mine && ((b0.level[e] == 0) == (mybit == 1));
         }
@@ -423,6 +467,43 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         }
         groups.push_back(g);
     }
+    return 0;
+}
+
+// flat sweep tables: for every multi-cell (device-layout cell index) and direction d its pole group, item and 1-D cell
+int host_flat_cells(const gsg::IndexSet& S, int d, const std::vector<GroupDev>& groups, std::vector<FlatCell>& cells /* ncells * D */) {
+    const int D = S.D;
+    const long long KDp = S.kDp;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const GroupDev& g = groups[gi];
+        for (int ld = 0; ld <= g.p; ++ld) {
+            const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+            const int q0 = ld == 0 ? 0 : 1 << (ld - 1);
+            if (g.base[ld] % KDp != 0) return fail(GSG_ERR_UNSUPPORTED, "internal: unaligned block");
+            const long long cell0 = g.base[ld] / KDp;
+            for (int r = 0; r < g.nitems; ++r) {
+                const long long lo = r % g.S, hi = r / g.S;
+                for (int cd = 0; cd < Cd; ++cd) {
+                    const long long ci = cell0 + lo + (long long)g.S * (cd + (long long)Cd * hi);
+                    if (ci < 0 || ci >= S.ncells_total) return fail(GSG_ERR_UNSUPPORTED, "internal: flat cell index out of range");
+                    cells[(size_t)ci * D + d] = FlatCell{(int)gi, r, q0 + cd};
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_np /* -1: keep every group */) {
+    const gsg::IndexSet& S = P.S;
+    const int K = S.k, n = S.n;
+    dir.A = pow_int(K, d);
+    const int KD = (int)S.kD, KDp = (int)S.kDp;
+    const int PI = KD / K;
+
+    std::vector<GroupDev> groups;
+    GSG_TRY(host_groups(S, d, P.part_rank, P.part_bits, exclude_np, groups));
+    dir.groups_h = groups;
     GSG_TRY(dir.groups.upload(groups));
 
     // ---- merged TMA class for all register-resident pole lengths
@@ -941,9 +1022,10 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         const int grid = std::max(1, std::min(pl.sm_count, std::min(tn, std::max(8, tn / 12))));
         static_assert(sizeof(HDense<K>) + 256 < 32000, "dense blocks must fit the kernel parameter space");
         HDense<K> hd;
-        if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
+        const std::vector<double>& dense = pl.use_sq ? pl.dense_sq_host : pl.dense_host;     // Laplacian: pre-squared blocks
+        if ((int)dense.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
-        std::memcpy(hd.v, pl.dense_host.data(), sizeof(hd.v));
+        std::memcpy(hd.v, dense.data(), sizeof(hd.v));
         int* const counter = pl.tile_counter.p + (pl.ctr_next++ & 63);       // launches may overlap: one slot each
         GSG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
@@ -1081,6 +1163,10 @@ int launch_generic_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
     static thread_local size_t configured = 0;
     GSG_TRY(ensure_smem(kern, c.smem, configured));
     Bcsr M{pl.b_rowptr.p, pl.b_col.p, pl.b_val.p, pl.KK2};
+    if (pl.use_sq) {                       // Laplacian: the class's own pre-squared rows
+        if (c.p > pl.sq_pmax) return fail(GSG_ERR_UNSUPPORTED, "internal: no squared blocks for this class");
+        M = Bcsr{pl.sq_rowptr.p + pl.sq_cls_row0[c.p], pl.sq_col.p, pl.sq_val.p, pl.KK2};
+    }
     int tb, tn;
     tile_range(pl, c.ntiles, tb, tn);
     if (tn == 0) return 0;
@@ -1119,6 +1205,86 @@ int elementwise_grid(const gsg_plan& pl, int64_t N) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)pl.sm_count * 16));
 }
 
+// ---- flat path: one launch per right-hand side for small index sets (kernels.cuh, sweep_flat_kernel) ----------
+constexpr int64_t FLAT_AUTO_MAX = 6000000;       // automatic mode: N * D up to this (launch-latency regime)
+
+bool flat_supported(const gsg_plan& pl) {
+    return pl.S.k >= 1 && pl.S.k <= 5 && pl.S.D <= FLAT_MAXD && pl.part_bits == 0 && pl.S.ncells_total < 0x7fffffffLL;
+}
+
+bool flat_on(const gsg_plan& pl) {
+    if (pl.flat_mode == 0 || !flat_supported(pl)) return false;
+    return pl.flat_mode == 1 || pl.S.N * pl.S.D <= FLAT_AUTO_MAX;
+}
+
+int flat_tables(gsg_plan& pl) {
+    if (pl.flat_cells.p) return 0;
+    std::vector<FlatCell> cells((size_t)pl.S.ncells_total * pl.S.D, FlatCell{-1, 0, 0});
+    for (int d = 0; d < pl.S.D; ++d) GSG_TRY(host_flat_cells(pl.S, d, pl.dirs[d].groups_h, cells));
+    for (const FlatCell& c : cells)
+        if (c.group < 0) return fail(GSG_ERR_UNSUPPORTED, "internal: flat table does not cover every cell");
+    return pl.flat_cells.upload(cells);
+}
+
+template <int K>
+int launch_flat_k(gsg_plan& pl, const FlatDirs& fd, const FlatMat& M, const double* x, double* y, double beta, int pmin, int pmax) {
+    if constexpr (K >= 1 && K <= 5) {
+        const int PI = (int)pl.S.kD / K;
+        int G = 32;
+        while (G > 4 && G * PI > FLAT_THREADS) G >>= 1;
+        const int cpc = std::max(1, (FLAT_THREADS / G) / PI);
+        const int ncells = (int)pl.S.ncells_total;
+        const int grid = (ncells + cpc - 1) / cpc;
+        const size_t smem = (size_t)cpc * pl.S.kDp * sizeof(double);
+        auto kern = sweep_flat_kernel<K>;
+        if (smem > 48 * 1024) GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
+        if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, pl.stream));
+        kern<<<grid, FLAT_THREADS, smem, pl.stream>>>(x, y, beta, fd, pl.flat_cells.p, pl.S.D, ncells, cpc, M, (int)pl.S.kD,
+                                                       (int)pl.S.kDp, PI, G, pmin, pmax);
+        if (prof) {
+            GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, pl.stream));
+            ++pl.prof_used;
+            pl.prof_dofs += (double)pl.S.N * fd.ndir;        // directional applies' worth of DOFs
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        GSG_CUDA(cudaGetLastError());
+        return 0;
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: flat kernel not instantiated");
+}
+
+// y = beta * y + sum_{d in mask, c_d != 0} c_d M_d x on the poles of class pmin..pmax; M = the derivative blocks or
+// (sq) the pre-squared blocks of the short classes
+int flat_apply(gsg_plan& pl, const double* c, unsigned mask, const double* x, double* y, double beta, bool sq = false,
+               int pmin = 0, int pmax = MAXL) {
+    nvtx_range nvtx_r("rhs: flat");
+    GSG_TRY(flat_tables(pl));
+    const int K = pl.S.k;
+    FlatDirs fd;
+    std::memset(&fd, 0, sizeof(fd));
+    for (int d = 0; d < pl.S.D; ++d) {
+        if (!((mask >> d) & 1) || c[d] == 0.0) continue;
+        fd.groups[fd.ndir] = pl.dirs[d].groups.p;
+        fd.c[fd.ndir] = c[d];
+        fd.A[fd.ndir] = pl.dirs[d].A;
+        fd.d[fd.ndir] = d;
+        ++fd.ndir;
+    }
+    FlatMat M;
+    std::memset(&M, 0, sizeof(M));
+    M.KK2 = pl.KK2;
+    if (sq) {
+        if (pmax > pl.sq_pmax) return fail(GSG_ERR_UNSUPPORTED, "internal: squared blocks exist for the short classes only");
+        M.rowptr = pl.sq_rowptr.p; M.col = pl.sq_col.p; M.val = pl.sq_val.p;
+        for (int p = 0; p <= pl.sq_pmax; ++p) M.cls_row0[p] = pl.sq_cls_row0[p];
+    } else {
+        M.rowptr = pl.b_rowptr.p; M.col = pl.b_col.p; M.val = pl.b_val.p;
+    }
+    GSG_K_SWITCH(launch_flat_k, pl, fd, M, x, y, beta, pmin, pmax);
+    return fail(GSG_ERR_UNSUPPORTED, "internal: flat kernel for k > 5");
+}
+
 // y = alpha * D_d x + beta * y   (d 0-based; device layout); x and y must not alias.  The launches
 // of one sweep write disjoint parts of y, so they are forked onto auxiliary streams and joined.
 int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, double* y, bool reduced = false) {
@@ -1126,6 +1292,19 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
                                           "sweep d=7", "sweep d=8", "sweep d=9", "sweep d=10", "sweep d=11", "sweep d=12",
                                           "sweep", "sweep", "sweep", "sweep"};
     nvtx_range nvtx_r(names[d & 15]);
+    if (!reduced && pl.kind_filter == 0 && !pl.use_sq && flat_on(pl)) {
+        double c[FLAT_MAXD] = {0};
+        c[d] = alpha;
+        if (alpha == 0.0) {                  // y = beta * y
+            if (beta == 0.0) GSG_CUDA(cudaMemsetAsync(y, 0, (size_t)pl.S.Npad * sizeof(double), pl.stream));
+            else if (beta != 1.0) {
+                scale_kernel<<<elementwise_grid(pl, pl.S.Npad), 256, 0, pl.stream>>>(pl.S.Npad, y, beta);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            return 0;
+        }
+        return flat_apply(pl, c, 1u << d, x, y, beta);
+    }
     const Direction& dir = reduced ? pl.dirs_red[d] : pl.dirs[d];
     const size_t nc = dir.classes.size();
     if (beta != 0.0 && beta != 1.0) {     // kernels implement beta in {0, 1}
@@ -1144,7 +1323,12 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     static const int only = getenv("GSG_ONLY_CLASS") ? atoi(getenv("GSG_ONLY_CLASS")) : -1;   // timing aid
     static const int cmask = getenv("GSG_CLASS_MASK") ? atoi(getenv("GSG_CLASS_MASK")) : -1;  // timing aid (bit i = class i)
     static const bool stream_first = getenv("GSG_STREAM_FIRST") != nullptr;
-    if (stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1)))
+    // Laplacian passes (kind_filter): 1 = only the classes that have pre-squared blocks, 2 = only the others
+    auto keep = [&](size_t i) {
+        const bool shortc = dir.classes[i].p <= pl.sq_pmax;
+        return pl.kind_filter == 0 || (pl.kind_filter == 1 ? shortc : !shortc);
+    };
+    if (stream_first && nc > 0 && keep(0) && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1)))
         GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
     // GSG_CONSTH_LAST: the constant-bank class is launched AFTER the streaming kernel (its small CTAs can
     // share an SM with a streaming CTA when the latter runs three stages)
@@ -1152,14 +1336,15 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
     for (size_t i = 1; i < nc; ++i) {
         if (only >= 0 && (int)i != only) continue;
         if (cmask >= 0 && !((cmask >> i) & 1)) continue;
+        if (!keep(i)) continue;
         if (consth_last && dir.classes[i].kind == Kind::CONSTH) continue;
         cudaStream_t st = fork ? pl.aux[i] : pl.stream;
         GSG_TRY(launch_class(pl, st, dir, dir.classes[i], x, y, alpha, beta));
     }
-    if (!stream_first && nc > 0 && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1))) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
+    if (!stream_first && nc > 0 && keep(0) && (only < 0 || only == 0) && (cmask < 0 || (cmask & 1))) GSG_TRY(launch_class(pl, pl.stream, dir, dir.classes[0], x, y, alpha, beta));
     if (consth_last)
         for (size_t i = 1; i < nc; ++i) {
-            if (dir.classes[i].kind != Kind::CONSTH) continue;
+            if (dir.classes[i].kind != Kind::CONSTH || !keep(i)) continue;
             if (only >= 0 && (int)i != only) continue;
             if (cmask >= 0 && !((cmask >> i) & 1)) continue;
             cudaStream_t st = fork ? pl.aux[i] : pl.stream;
@@ -1178,6 +1363,7 @@ int sweep(gsg_plan& pl, int d, double alpha, const double* x, double beta, doubl
 // y = beta0 * y + sum_{d in mask} c_d D_d x with the streaming classes of each direction pair fused (PAIR tiles)
 // where both directions of the pair are in the mask; every c_d in the mask must be non-zero
 int grad_fused(gsg_plan& pl, const double* c, const double* x, double* y, unsigned mask = ~0u, double beta0 = 0.0) {
+    if (flat_on(pl)) return flat_apply(pl, c, mask, x, y, beta0);
     nvtx_range nvtx_r("rhs: fused gradient");
     const int K = pl.S.k, D = pl.S.D;
     const int npairs = (int)pl.pairs.size();
@@ -1280,6 +1466,7 @@ int sweep_scatter(gsg_plan& pl, PoolCtx& ctx, int d, double alpha, const double*
 
 int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x, double* y, double beta0,
                    const cudaEvent_t* pre_wait = nullptr) {
+    if (!pre_wait && flat_on(pl)) return flat_apply(pl, c, mask, x, y, beta0);
     nvtx_range nvtx_r("rhs: concurrent");
     const int K = pl.S.k, D = pl.S.D;
     if (beta0 != 0.0 && beta0 != 1.0) return fail(GSG_ERR_ARG, "beta must be 0 or 1");
@@ -1381,10 +1568,53 @@ int advect_rhs(gsg_plan& pl, const double* a, const double* w, double* k) {
 }
 
 // k = sum_d D_d (D_d u)
+// The reference applies the explicit product: lap += D_op * D_op, then lap * x (src/multidim_derivative.jl:71-79).
+// Restricted to a pole, D_op * D_op is the square of the pole's principal sub-block, so the short classes
+// (p <= sq_pmax, dense blocks anyway) take ONE sweep with the pre-squared blocks S_p -- half the traffic and the
+// reference's rounding.  For the long classes the square is completely dense (level 0 touches every cell: 65 536
+// blocks instead of 5 308 at k = 3, n = 8), so those poles stay two sparse applications D_d (D_d x).
 int laplacian(gsg_plan& pl, const double* u, double* k, double* tmp) {
-    for (int d = 0; d < pl.S.D; ++d) {
-        GSG_TRY(sweep(pl, d, 1.0, u, 0.0, tmp));
-        GSG_TRY(sweep(pl, d, 1.0, tmp, d == 0 ? 0.0 : 1.0, k));
+    nvtx_range nvtx_r("rhs: laplacian");
+    const int D = pl.S.D;
+    static const bool nosq = getenv("GSG_LAP_NOSQ") != nullptr;
+    if (nosq || pl.sq_pmax < 0) {
+        for (int d = 0; d < D; ++d) {
+            GSG_TRY(sweep(pl, d, 1.0, u, 0.0, tmp));
+            GSG_TRY(sweep(pl, d, 1.0, tmp, d == 0 ? 0.0 : 1.0, k));
+        }
+        return 0;
+    }
+    const bool any_long = pl.S.n > pl.sq_pmax;
+    const bool any_short = pl.S.scheme == 0 || pl.S.n <= pl.sq_pmax;      // full scheme: every pole has p = n
+    if (flat_on(pl)) {
+        double ones[FLAT_MAXD];
+        for (int d = 0; d < FLAT_MAXD; ++d) ones[d] = 1.0;
+        // every cell is written here (zero where a cell has no short pole), the long passes accumulate
+        GSG_TRY(flat_apply(pl, ones, ~0u, u, k, 0.0, true, 0, pl.sq_pmax));
+        if (any_long)
+            for (int d = 0; d < D; ++d) {
+                GSG_TRY(flat_apply(pl, ones, 1u << d, u, tmp, 0.0, false, pl.sq_pmax + 1, MAXL));
+                GSG_TRY(flat_apply(pl, ones, 1u << d, tmp, k, 1.0, false, pl.sq_pmax + 1, MAXL));
+            }
+        return 0;
+    }
+    struct Restore {
+        gsg_plan& pl;
+        ~Restore() { pl.use_sq = false; pl.kind_filter = 0; }
+    } restore{pl};
+    for (int d = 0; d < D; ++d) {
+        const double beta = d == 0 ? 0.0 : 1.0;
+        if (any_short) {
+            pl.use_sq = true;
+            pl.kind_filter = 1;
+            GSG_TRY(sweep(pl, d, 1.0, u, beta, k));
+        }
+        if (any_long) {
+            pl.use_sq = false;
+            pl.kind_filter = 2;
+            GSG_TRY(sweep(pl, d, 1.0, u, 0.0, tmp));
+            GSG_TRY(sweep(pl, d, 1.0, tmp, beta, k));
+        }
     }
     return 0;
 }
@@ -1660,6 +1890,7 @@ int gsg_plan_create(int D, int k, int n, int scheme, int64_t H_n, const int64_t*
         GSG_CUDA(cudaEventCreateWithFlags(&P->pool_ev[i], cudaEventDisableTiming));
     }
     GSG_CUDA(cudaEventCreateWithFlags(&P->ev_p1, cudaEventDisableTiming));
+    if (const char* e = getenv("GSG_FLAT")) P->flat_mode = std::max(0, std::min(2, atoi(e)));
     GSG_TRY(build_matrix(*P, H_n, H_colptr, H_rowval, H_nzval));
     P->dirs.resize(D);
     for (int d = 0; d < D; ++d) GSG_TRY(build_direction(*P, d, P->dirs[d], -1));
@@ -1737,6 +1968,45 @@ int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_lay
     GSG_TRY(check_plan(plan));
     if (!ref_layout_dev || !dev_layout_dev) return fail(GSG_ERR_ARG, "null pointer");
     return copy_out(*plan, ref_layout_dev, dev_layout_dev, cudaMemcpyDeviceToDevice);
+}
+
+int gsg_plan_flat_active(const gsg_plan* plan, int* active_out) {
+    if (!plan || !active_out) return fail(GSG_ERR_ARG, "null pointer");
+    *active_out = flat_on(*plan) ? 1 : 0;
+    return 0;
+}
+
+int gsg_plan_set_flat(gsg_plan* plan, int mode) {
+    if (!plan || mode < 0 || mode > 2) return fail(GSG_ERR_ARG, "flat mode must be 0 (tiled), 1 (flat) or 2 (automatic)");
+    plan->flat_mode = mode;
+    return 0;
+}
+
+int gsg_debug_flat_tables(int D, int k, int n, int scheme, int d, int64_t* groups_out, int32_t* cells_out,
+                          int64_t* ngroups_out, int64_t* ncells_out) {
+    GSG_TRY(check_dkn(D, k, n, scheme));
+    if (d < 1 || d > D) return fail(GSG_ERR_ARG, "axis d out of range [1,D]");
+    gsg::IndexSet S;
+    if (!S.build(D, k, n, scheme)) return fail(GSG_ERR_UNSUPPORTED, "index set too large");
+    std::vector<GroupDev> groups;
+    GSG_TRY(host_groups(S, d - 1, 0, 0, -1, groups));
+    if (ngroups_out) *ngroups_out = (int64_t)groups.size();
+    if (ncells_out) *ncells_out = S.ncells_total;
+    if (groups_out)
+        for (size_t g = 0; g < groups.size(); ++g) {
+            int64_t* o = groups_out + g * 20;
+            for (int l = 0; l <= MAXL; ++l) o[l] = groups[g].base[l];
+            o[17] = groups[g].p; o[18] = groups[g].S; o[19] = groups[g].nitems;
+        }
+    if (cells_out) {
+        std::vector<FlatCell> cells((size_t)S.ncells_total * D, FlatCell{-1, 0, 0});
+        GSG_TRY(host_flat_cells(S, d - 1, groups, cells));
+        for (int64_t c = 0; c < S.ncells_total; ++c) {
+            const FlatCell& fc = cells[(size_t)c * D + (d - 1)];
+            cells_out[3 * c] = fc.group; cells_out[3 * c + 1] = fc.r; cells_out[3 * c + 2] = fc.q;
+        }
+    }
+    return 0;
 }
 
 int gsg_plan_set_rk4_mode(gsg_plan* plan, int mode) {

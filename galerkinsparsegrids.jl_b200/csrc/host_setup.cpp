@@ -397,6 +397,18 @@ Csc periodic_hier_DLF_matrix(int k, int max_level) {
     return spmatmul(transpose(Q), spmatmul(A, Q));
 }
 
+void dense_square(const double* A, int n, double* C) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double prod = A[(size_t)i * n + k] * A[(size_t)k * n + j];
+                acc = acc + prod;
+            }
+            C[(size_t)i * n + j] = acc;
+        }
+}
+
 // ------------------------------------------------------------------------------------------
 bool IndexSet::build(int D_, int k_, int n_, int scheme_) {
     D = D_; k = k_; n = n_; scheme = scheme_;

@@ -39,6 +39,9 @@ Csc periodic_pos_DLF_matrix(int k, int max_level);           // src/1d_derivativ
 Csc periodic_hier_DLF_matrix(int k, int max_level);          // src/1d_derivative.jl:113-117
 Csc spmatmul(const Csc& A, const Csc& B);                    // SparseArrays.spmatmul (Gustavson)
 Csc transpose(const Csc& A);
+// C = A * A for a dense row-major n x n block, inner index ascending, separate multiply and add (the order and
+// rounding of SparseArrays' A*B on the stored entries; zeros add nothing)   // src/multidim_derivative.jl:76
+void dense_square(const double* A, int n, double* C);
 
 // ---- index set / layout -------------------------------------------------------------------
 struct Block {

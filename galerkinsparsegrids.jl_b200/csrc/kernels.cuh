@@ -21,6 +21,7 @@
 //   sweep_long2_kernel<K, C, NB>   N' >= 96   register-tiled: lanes = poles, C poles per lane, record stream
 //   sweep_short_tma_kernel (small k^D: many multi-cells per tile), sweep_generic_kernel (any k <= 10, any length)
 //   rk_stage_kernel, rk_final_kernel, rk4_taylor_kernel(_cells)   RK4 updates
+//   sweep_flat_kernel<K>           small index sets: one launch per right-hand side, all directions, no atomics
 //   reconstruct2_kernel (reconstruct_kernel)   batched reconstruct_DG;   spmv_csr_kernel   cross-check SpMV
 #pragma once
 #include <cuda_runtime.h>
@@ -1801,6 +1802,118 @@ __global__ void recon_keys_kernel(const double* __restrict__ pts, long long npts
     }
     keys[i] = key;
     vals[i] = (unsigned)i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Flat sweep for SMALL index sets (launch-latency regime: BASELINE configs 2 and 3, N = 1e4 .. 3e5): ONE launch
+// computes  y = beta * y + sum_{d in list} c_d * M_d x  for every direction of the list, with no atomics and no
+// tiling by pole class.  A CTA owns `cpc` consecutive multi-cells and accumulates their k^D outputs in shared
+// memory; for each direction a group of G lanes owns one (cell, pole) unit = K outputs, walks the block row of
+// the unit's 1-D cell (block CSR of the 1-D matrix, truncated to the principal sub-block of the pole's class)
+// with the lanes striding the records, gathers x straight from global memory (the whole state of these
+// configurations sits in L2) and reduces over the G lanes.  Directions are separated by a CTA barrier because the
+// unit <-> output mapping changes with the direction.
+//   FlatCell (per multi-cell and direction): pole group, item and 1-D cell of the multi-cell along that direction.
+//   FlatMat: block CSR per pole class -- row q of class p is rowptr[cls_row0[p] + q]; for the derivative every
+//   class uses the same rows (principal sub-blocks: stop at col >= 2^p); for the pre-squared Laplacian blocks
+//   S_p = (H[0:N',0:N'])^2 (src/multidim_derivative.jl:71-79) every class has its own rows.
+//   Only units whose class lies in [pmin, pmax] are processed.
+// ------------------------------------------------------------------------------------------
+struct FlatCell {
+    int group, r, q;
+};
+
+constexpr int FLAT_MAXD = 12;
+
+struct FlatDirs {
+    const GroupDev* groups[FLAT_MAXD];
+    double c[FLAT_MAXD];
+    int A[FLAT_MAXD];
+    int d[FLAT_MAXD];
+    int ndir;
+};
+
+struct FlatMat {
+    const int* rowptr;
+    const int* col;
+    const double* val;
+    int KK2;
+    int cls_row0[MAXL + 1];
+};
+
+constexpr int FLAT_THREADS = 128;
+
+template <int K>
+__global__ void __launch_bounds__(FLAT_THREADS)
+sweep_flat_kernel(const double* __restrict__ X, double* __restrict__ Y, double beta, const FlatDirs fd,
+                  const FlatCell* __restrict__ cells, int D, int ncells, int cpc, const FlatMat M, int KD, int KDp,
+                  int PI, int G, int pmin, int pmax) {
+    extern __shared__ __align__(16) double acc_s[];          // cpc * KDp
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int c0 = blockIdx.x * cpc;
+    const int nc = min(cpc, ncells - c0);
+    for (int i = tid; i < nc * KDp; i += nth) acc_s[i] = 0.0;
+    __syncthreads();
+    const int g = tid & (G - 1), ugrp = tid / G, ngrp = nth / G;
+    const int nunits = nc * PI;
+    for (int di = 0; di < fd.ndir; ++di) {
+        const int A = fd.A[di], dd = fd.d[di];
+        const double cd = fd.c[di];
+        const GroupDev* __restrict__ groups = fd.groups[di];
+        for (int u0 = 0; u0 < nunits; u0 += ngrp) {          // uniform trip count: every lane reaches the shuffles
+            const int u = u0 + ugrp;
+            double acc[K];
+#pragma unroll
+            for (int m = 0; m < K; ++m) acc[m] = 0.0;
+            int cl = 0, po = 0;
+            bool live = false;
+            if (u < nunits) {
+                cl = u / PI;
+                const int j = u - cl * PI;
+                const int b = j / A, a = j - b * A;
+                po = a + K * A * b;
+                const FlatCell fc = cells[(size_t)(c0 + cl) * D + dd];
+                const GroupDev* gr = groups + fc.group;
+                const int p = gr->p;
+                live = p >= pmin && p <= pmax;
+                if (live) {
+                    const int NQ = 1 << p, S = gr->S;
+                    const int lo = fc.r % S, hi = fc.r / S;
+                    const int rb = M.cls_row0[p] + fc.q;
+                    const int r1 = __ldg(M.rowptr + rb + 1);
+                    for (int rec = __ldg(M.rowptr + rb) + g; rec < r1; rec += G) {
+                        const int qc = __ldg(M.col + rec);
+                        if (qc >= NQ) break;                 // block columns ascend: the rest lies outside the sub-block
+                        int ld, cdv, Cd;
+                        q_decode(qc, ld, cdv, Cd);
+                        const double* xv = X + gr->base[ld] + (long long)KDp * (lo + (long long)S * (cdv + (long long)Cd * hi)) + po;
+                        const double* hv = M.val + (size_t)rec * M.KK2;
+                        double xr[K];
+#pragma unroll
+                        for (int mi = 0; mi < K; ++mi) xr[mi] = xv[A * mi];
+#pragma unroll
+                        for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                            for (int mi = 0; mi < K; ++mi) acc[mo] = fma(__ldg(hv + mo * K + mi), xr[mi], acc[mo]);
+                    }
+                }
+            }
+            __syncwarp();
+            for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int m = 0; m < K; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+            }
+            if (live && g == 0) {
+#pragma unroll
+                for (int m = 0; m < K; ++m) acc_s[cl * KDp + po + A * m] += cd * acc[m];
+            }
+        }
+        __syncthreads();
+    }
+    double* yo = Y + (size_t)c0 * KDp;
+    for (int i = tid; i < nc * KDp; i += nth) {
+        if (i % KDp < KD) yo[i] = beta == 0.0 ? acc_s[i] : fma(beta, yo[i], acc_s[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

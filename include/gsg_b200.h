@@ -97,13 +97,27 @@ int gsg_unpack_dev(gsg_plan* plan, const double* dev_layout_dev, double* ref_lay
 /* run all subsequent work of this plan on `stream` (cudaStream_t); NULL = the plan's own */
 int gsg_plan_set_stream(gsg_plan* plan, void* stream);
 int gsg_plan_sync(gsg_plan* plan);
+/* Execution path of the operator applies.  mode 0: the tiled class kernels (streaming / long-pole) always;
+ * 1: the flat kernel (one launch per right-hand side, all directions) whenever it supports the plan (k <= 5,
+ * no partition); 2 (default): automatic -- flat for small index sets (N * D <= 6e6: BASELINE configs 2 and 3,
+ * where a step is launch-latency bound), tiled above.  The environment variable GSG_FLAT sets the initial mode. */
+int gsg_plan_set_flat(gsg_plan* plan, int mode);
+/* 1 if the operator applies of this plan currently take the flat kernel */
+int gsg_plan_flat_active(const gsg_plan* plan, int* active_out);
+/* CPU-side check of the flat path's tables (no device needed): pole groups of direction d (1-based) and, for
+ * every multi-cell of the device layout, its {group, item, 1-D cell} along d.  groups_out: ngroups rows of
+ * 20 int64 {base[0..16], p, S, nitems}; cells_out: ncells rows of 3 int32.  Pass NULL outputs to query the
+ * counts (ngroups_out, ncells_out). */
+int gsg_debug_flat_tables(int D, int k, int n, int scheme, int d, int64_t* groups_out, int32_t* cells_out,
+                          int64_t* ngroups_out, int64_t* ncells_out);
 
 /* ---- operator apply, host vectors (drop-in for `A*x`) ------------------------------------ */
 /* y = D_d * x             `Ds[d] * f_modal`  src/pdes.jl:179-180, `D_ops[j]*u` :268 */
 int gsg_apply_D(gsg_plan* plan, int d, const double* x, double* y);
 /* y = sum_d a[d] * D_d x  (gradient combination; a has D entries) */
 int gsg_apply_grad(gsg_plan* plan, const double* a, const double* x, double* y);
-/* y = sum_d D_d (D_d x)   `laplacian_matrix(D,k,n) * x`  src/multidim_derivative.jl:71-79 */
+/* y = (sum_d D_d * D_d) x   `laplacian_matrix(D,k,n) * x`  src/multidim_derivative.jl:71-79: the short pole
+ * classes apply the explicit square of their block (the reference's form), the long ones D_d (D_d x) */
 int gsg_apply_laplacian(gsg_plan* plan, const double* x, double* y);
 
 /* ---- operator apply, device vectors (DEVICE LAYOUT, length gsg_plan_dev_size) ---------------- */

@@ -33,9 +33,13 @@ CASES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def plans(gsg, oracle):
+# every test that takes `plans` runs twice: through the tiled class kernels (streaming / constant-bank /
+# register-tiled / generic) and through the flat kernel (one launch per right-hand side; what small index sets
+# take by default).  k = 6 has no flat instantiation: its "flat" run exercises the fall-through to the tiled path.
+@pytest.fixture(scope="module", params=[0, 1], ids=["tiled", "flat"])
+def plans(gsg, oracle, request):
     cache = {}
+    mode = request.param
 
     def get(D, k, n, scheme):
         key = (D, k, n, scheme)
@@ -44,9 +48,12 @@ def plans(gsg, oracle):
             import scipy.sparse as sp
             Hs = sp.csc_matrix((H.nzval, H.rowval, H.colptr), shape=(H.m, H.n))
             # the SAME 1-D matrix is handed to the GPU plan and to the oracle
-            cache[key] = (gsg.Plan(D, k, n, scheme, H=Hs), H)
+            plan = gsg.Plan(D, k, n, scheme, H=Hs)
+            plan.set_flat(mode)
+            cache[key] = (plan, H)
         return cache[key]
 
+    get.mode = mode
     return get
 
 
@@ -150,6 +157,8 @@ def test_rk4_wave_fixed_steps(plans, oracle):
 @pytest.mark.parametrize("D,k,n,scheme", [(1, 3, 5, "sparse"), (2, 3, 4, "sparse"), (2, 2, 3, "full"),
                                           (3, 4, 3, "sparse"), (4, 3, 3, "sparse")])
 def test_reconstruct(plans, oracle, D, k, n, scheme):
+    if plans.mode == 1:
+        pytest.skip("reconstruct does not depend on the sweep path")
     plan, _ = plans(D, k, n, scheme)
     vect = product_state(oracle, D, k, n, f_sin, scheme=scheme) + 0.1 * product_state(oracle, D, k, n, f_gauss, scheme=scheme)
     rng = np.random.default_rng(20240)
@@ -165,6 +174,8 @@ def test_reconstruct(plans, oracle, D, k, n, scheme):
 
 
 def test_reconstruct_empty_and_single(plans, oracle):
+    if plans.mode == 1:
+        pytest.skip("reconstruct does not depend on the sweep path")
     plan, _ = plans(2, 3, 4, "sparse")
     vect = product_state(oracle, 2, 3, 4, f_cos)
     assert plan.reconstruct(vect, np.empty((0, 2))).shape == (0,)
@@ -352,3 +363,32 @@ def test_fused_gradient_matches_unfused(plans, oracle, D, k, n):
     a0[0] = 0.0
     ref0 = sum(a0[d - 1] * oracle.apply_D_poles(D, d, k, n, x, H=H) for d in range(1, D + 1))
     assert relerr(plan.apply_grad(a0, x), ref0) <= TOL
+
+
+@pytest.mark.parametrize("D,k,n,scheme", [(3, 3, 4, "sparse"), (2, 2, 5, "sparse"), (4, 3, 3, "sparse"), (2, 4, 3, "full")])
+def test_device_pointer_applies_alpha_beta_masks(plans, oracle, D, k, n, scheme):
+    """gsg_apply_D_dev with general alpha / beta, gsg_apply_dirs_dev with direction masks and beta = 1, and the
+    padding slots of the device layout staying zero -- on both sweep paths."""
+    import torch
+    plan, H = plans(D, k, n, scheme)
+    x = random_state(plan.size, seed=31)
+    y0 = random_state(plan.size, seed=32)
+    xd, yd = plan.to_device(x), plan.to_device(y0)
+    Dx = [oracle.apply_D_poles(D, d, k, n, x, scheme=scheme, H=H) for d in range(1, D + 1)]
+    plan.apply_D_dev(D, xd, yd, alpha=-0.75, beta=0.5)
+    assert relerr(plan.to_host(yd), -0.75 * Dx[D - 1] + 0.5 * y0) <= TOL
+    yd = plan.to_device(y0)
+    plan.apply_D_dev(1, xd, yd, alpha=2.0, beta=1.0)
+    assert relerr(plan.to_host(yd), 2.0 * Dx[0] + y0) <= TOL
+    c = np.linspace(-1.0, 2.0, D)
+    dirs = [d for d in range(1, D + 1) if d != 2]
+    yd = plan.to_device(y0)
+    plan.apply_dirs_dev(c, dirs, xd, yd, beta=1.0)
+    ref = y0 + sum(c[d - 1] * Dx[d - 1] for d in dirs)
+    assert relerr(plan.to_host(yd), ref) <= TOL
+    plan.apply_dirs_dev(c, range(1, D + 1), xd, yd, beta=0.0)
+    assert relerr(plan.to_host(yd), sum(c[d - 1] * Dx[d - 1] for d in range(1, D + 1))) <= TOL
+    plan.sync()
+    KD, KDp = k ** D, plan.cell_stride
+    if KDp > KD:
+        assert float(torch.abs(yd.view(-1, KDp)[:, KD:]).max()) == 0.0

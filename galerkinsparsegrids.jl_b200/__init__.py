@@ -415,6 +415,7 @@ class Plan:
                 raise ValueError("tensor_construct: 1-D vectors must have length k*2^n")
         arr = (C.c_void_p * self.D)(*[v.ctypes.data for v in vs])
         out = torch.zeros(self.dev_size, dtype=torch.float64, device=device if device is not None else "cuda")
+        torch.cuda.current_stream(out.device).synchronize()      # the fill runs on torch's stream, the expansion on the plan's
         check(lib.gsg_tensor_construct_dev(self._h, arr, _devptr(out)))
         return out
 
@@ -423,6 +424,7 @@ class Plan:
         import torch
         ref = torch.from_numpy(self._vec(host_vec)).to(device)
         dev = torch.zeros(self.dev_size, dtype=torch.float64, device=device)
+        torch.cuda.current_stream(dev.device).synchronize()      # copy and fill run on torch's stream, the pack on the plan's
         self.pack_dev(ref, dev)
         self.sync()
         return dev
@@ -430,6 +432,7 @@ class Plan:
     def to_host(self, dev_vec) -> np.ndarray:
         import torch
         ref = torch.empty(self.size, dtype=torch.float64, device=dev_vec.device)
+        torch.cuda.current_stream(dev_vec.device).synchronize()  # work torch may still have queued on dev_vec
         self.unpack_dev(dev_vec, ref)
         self.sync()
         return ref.cpu().numpy()

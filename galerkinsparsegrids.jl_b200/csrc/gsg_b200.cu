@@ -79,6 +79,10 @@ struct DevBuf {                       // move-only owner of a device allocation
         if (n == 0) return 0;
         GSG_CUDA(cudaMalloc(&p, n * sizeof(T)));
         GSG_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        // a pageable host-to-device cudaMemcpy may return once the data is staged, before the DMA has landed; the plans'
+        // streams are non-blocking (not ordered behind the legacy stream), so a table built lazily right before a launch
+        // (flat tables, tensor_construct's cell table) must be waited for explicitly
+        GSG_CUDA(cudaStreamSynchronize(0));
         return 0;
     }
     // grow-only; new allocations are zero-filled (the padding slots of state vectors stay finite)
@@ -88,6 +92,9 @@ struct DevBuf {                       // move-only owner of a device allocation
         n = m;
         GSG_CUDA(cudaMalloc(&p, n * sizeof(T)));
         GSG_CUDA(cudaMemset(p, 0, n * sizeof(T)));
+        // cudaMemset on device memory is asynchronous (legacy stream) and the plans' streams are non-blocking: without
+        // this wait a kernel on the plan's stream could run before the fill and have its output zeroed afterwards
+        GSG_CUDA(cudaStreamSynchronize(0));
         return 0;
     }
 };
@@ -199,7 +206,8 @@ struct gsg_plan {
     // flat path (kernels.cuh, sweep_flat_kernel): one launch per right-hand side for small index sets.
     // flat_mode: 0 = never, 1 = whenever supported, 2 = automatic (N * D <= FLAT_AUTO_MAX)
     int flat_mode = 2;
-    DevBuf<FlatCell> flat_cells;
+    DevBuf<int> flat_cd;                                   // FLATCD ints per (multi-cell, direction)
+    DevBuf<int> sq_rowend;
     // pre-squared Laplacian blocks S_p = (H[0:N',0:N'])^2 of the short classes p <= sq_pmax (dense there anyway;
     // for the long classes the square is completely dense -- level 0 touches every cell -- so those stay D(D x))
     int sq_pmax = -1;
@@ -369,6 +377,11 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
                 }
             }
             rp.push_back((int)cl.size());
+        }
+        {
+            std::vector<int> re(rp.size(), 0);
+            for (size_t i = 0; i + 1 < rp.size(); ++i) re[i] = rp[i + 1];
+            GSG_TRY(P.sq_rowend.upload(re));
         }
         GSG_TRY(P.sq_rowptr.upload(rp));
         GSG_TRY(P.sq_col.upload(cl));
@@ -1209,7 +1222,8 @@ int elementwise_grid(const gsg_plan& pl, int64_t N) {
 constexpr int64_t FLAT_AUTO_MAX = 6000000;       // automatic mode: N * D up to this (launch-latency regime)
 
 bool flat_supported(const gsg_plan& pl) {
-    return pl.S.k >= 1 && pl.S.k <= 5 && pl.S.D <= FLAT_MAXD && pl.part_bits == 0 && pl.S.ncells_total < 0x7fffffffLL;
+    return pl.S.k >= 1 && pl.S.k <= 5 && pl.S.D <= FLAT_MAXD && pl.part_bits == 0 && pl.S.ncells_total < 0x7fffffffLL &&
+           (size_t)FLAT_WARPS * pl.S.kDp * sizeof(double) <= 48 * 1024 && pl.S.n <= 15;
 }
 
 bool flat_on(const gsg_plan& pl) {
@@ -1218,30 +1232,56 @@ bool flat_on(const gsg_plan& pl) {
 }
 
 int flat_tables(gsg_plan& pl) {
-    if (pl.flat_cells.p) return 0;
-    std::vector<FlatCell> cells((size_t)pl.S.ncells_total * pl.S.D, FlatCell{-1, 0, 0});
-    for (int d = 0; d < pl.S.D; ++d) GSG_TRY(host_flat_cells(pl.S, d, pl.dirs[d].groups_h, cells));
-    for (const FlatCell& c : cells)
-        if (c.group < 0) return fail(GSG_ERR_UNSUPPORTED, "internal: flat table does not cover every cell");
-    return pl.flat_cells.upload(cells);
+    if (pl.flat_cd.p) return 0;
+    const gsg::IndexSet& S = pl.S;
+    const int D = S.D;
+    const long long KDp = S.kDp;
+    std::vector<FlatCell> cells((size_t)S.ncells_total * D, FlatCell{-1, 0, 0});
+    for (int d = 0; d < D; ++d) GSG_TRY(host_flat_cells(S, d, pl.dirs[d].groups_h, cells));
+    std::vector<int> tab((size_t)S.ncells_total * D * FLATCD, 0);
+    for (int64_t ci = 0; ci < S.ncells_total; ++ci)
+        for (int d = 0; d < D; ++d) {
+            const FlatCell& fc = cells[(size_t)ci * D + d];
+            if (fc.group < 0) return fail(GSG_ERR_UNSUPPORTED, "internal: flat table does not cover every cell");
+            const GroupDev& g = pl.dirs[d].groups_h[fc.group];
+            int* o = tab.data() + ((size_t)ci * D + d) * FLATCD;
+            // derivative blocks: class p ends row q at the first block column >= 2^p (principal sub-block)
+            int e = pl.h_rowptr[fc.q];
+            while (e < pl.h_rowptr[fc.q + 1] && pl.h_col[e] < (1 << g.p)) ++e;
+            o[0] = pl.h_rowptr[fc.q];
+            o[1] = e;
+            o[2] = g.S;
+            o[3] = (g.p << 16) | fc.q;
+            const long long lo = fc.r % g.S, hi = fc.r / g.S;
+            for (int l = 0; l <= g.p; ++l) {
+                const long long Cd = l <= 1 ? 1 : 1LL << (l - 1);
+                o[4 + l] = (int)(g.base[l] / KDp + lo + (long long)g.S * Cd * hi);
+            }
+        }
+    return pl.flat_cd.upload(tab);
 }
 
 template <int K>
 int launch_flat_k(gsg_plan& pl, const FlatDirs& fd, const FlatMat& M, const double* x, double* y, double beta, int pmin, int pmax) {
     if constexpr (K >= 1 && K <= 5) {
         const int PI = (int)pl.S.kD / K;
-        int G = 32;
-        while (G > 4 && G * PI > FLAT_THREADS) G >>= 1;
-        const int cpc = std::max(1, (FLAT_THREADS / G) / PI);
+        int PIp = 1;
+        while (PIp < PI && PIp < 32) PIp <<= 1;
+        const int nch = (PI + PIp - 1) / PIp;
+        const int nd = std::max(1, fd.ndir);
+        // cells per CTA: one when a cell fills half a warp's lanes with poles, else enough for ~8 items; record slices so
+        // that a CTA has ~16 items for its 8 warps (long rows -- the coarse cells -- are cut into more pieces)
+        int cpc = PI >= 16 ? 1 : std::max(1, std::min(8, (8 + nd * nch - 1) / (nd * nch)));
+        while (cpc > 1 && (size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double) > 48 * 1024) --cpc;
+        const int RS = std::max(1, std::min(8, 16 / (nd * nch * cpc)));
         const int ncells = (int)pl.S.ncells_total;
         const int grid = (ncells + cpc - 1) / cpc;
-        const size_t smem = (size_t)cpc * pl.S.kDp * sizeof(double);
-        auto kern = sweep_flat_kernel<K>;
-        if (smem > 48 * 1024) GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double);
+        auto kern = sweep_flat_kernel<K>;       // <= 48 KB of shared memory (flat_supported): the default carve-out keeps the L1 for the gathers
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, pl.stream));
-        kern<<<grid, FLAT_THREADS, smem, pl.stream>>>(x, y, beta, fd, pl.flat_cells.p, pl.S.D, ncells, cpc, M, (int)pl.S.kD,
-                                                       (int)pl.S.kDp, PI, G, pmin, pmax);
+        kern<<<grid, FLAT_THREADS, smem, pl.stream>>>(x, y, beta, fd, pl.flat_cd.p, pl.S.D, ncells, cpc, M, (int)pl.S.kD,
+                                                       (int)pl.S.kDp, PI, PIp, RS, pmin, pmax);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, pl.stream));
             ++pl.prof_used;
@@ -1265,7 +1305,6 @@ int flat_apply(gsg_plan& pl, const double* c, unsigned mask, const double* x, do
     std::memset(&fd, 0, sizeof(fd));
     for (int d = 0; d < pl.S.D; ++d) {
         if (!((mask >> d) & 1) || c[d] == 0.0) continue;
-        fd.groups[fd.ndir] = pl.dirs[d].groups.p;
         fd.c[fd.ndir] = c[d];
         fd.A[fd.ndir] = pl.dirs[d].A;
         fd.d[fd.ndir] = d;
@@ -1276,10 +1315,11 @@ int flat_apply(gsg_plan& pl, const double* c, unsigned mask, const double* x, do
     M.KK2 = pl.KK2;
     if (sq) {
         if (pmax > pl.sq_pmax) return fail(GSG_ERR_UNSUPPORTED, "internal: squared blocks exist for the short classes only");
-        M.rowptr = pl.sq_rowptr.p; M.col = pl.sq_col.p; M.val = pl.sq_val.p;
+        M.sq = 1;
+        M.rowptr = pl.sq_rowptr.p; M.rowend = pl.sq_rowend.p; M.col = pl.sq_col.p; M.val = pl.sq_val.p;
         for (int p = 0; p <= pl.sq_pmax; ++p) M.cls_row0[p] = pl.sq_cls_row0[p];
     } else {
-        M.rowptr = pl.b_rowptr.p; M.col = pl.b_col.p; M.val = pl.b_val.p;
+        M.col = pl.b_col.p; M.val = pl.b_val.p;       // row ranges come with the cell table
     }
     GSG_K_SWITCH(launch_flat_k, pl, fd, M, x, y, beta, pmin, pmax);
     return fail(GSG_ERR_UNSUPPORTED, "internal: flat kernel for k > 5");

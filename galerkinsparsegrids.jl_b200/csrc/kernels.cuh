@@ -1806,27 +1806,31 @@ __global__ void recon_keys_kernel(const double* __restrict__ pts, long long npts
 
 // ------------------------------------------------------------------------------------------
 // Flat sweep for SMALL index sets (launch-latency regime: BASELINE configs 2 and 3, N = 1e4 .. 3e5): ONE launch
-// computes  y = beta * y + sum_{d in list} c_d * M_d x  for every direction of the list, with no atomics and no
-// tiling by pole class.  A CTA owns `cpc` consecutive multi-cells and accumulates their k^D outputs in shared
-// memory; for each direction a group of G lanes owns one (cell, pole) unit = K outputs, walks the block row of
-// the unit's 1-D cell (block CSR of the 1-D matrix, truncated to the principal sub-block of the pole's class)
-// with the lanes striding the records, gathers x straight from global memory (the whole state of these
-// configurations sits in L2) and reduces over the G lanes.  Directions are separated by a CTA barrier because the
-// unit <-> output mapping changes with the direction.
-//   FlatCell (per multi-cell and direction): pole group, item and 1-D cell of the multi-cell along that direction.
-//   FlatMat: block CSR per pole class -- row q of class p is rowptr[cls_row0[p] + q]; for the derivative every
-//   class uses the same rows (principal sub-blocks: stop at col >= 2^p); for the pre-squared Laplacian blocks
-//   S_p = (H[0:N',0:N'])^2 (src/multidim_derivative.jl:71-79) every class has its own rows.
-//   Only units whose class lies in [pmin, pmax] are processed.
+// computes  y = beta * y + sum_{d in list} c_d * M_d x  for every direction of the list, with no global atomics and
+// no tiling by pole class.  A CTA owns `cpc` consecutive multi-cells.  Its warps share out the work items
+// (direction, cell, chunk of <= 32 poles, record slice): the lanes of a warp are the poles of the chunk (x is
+// gathered straight from global memory -- the whole state of these configurations sits in L2 -- and consecutive poles
+// read consecutive addresses), times 32 / PIp record sub-lanes when a cell has fewer than 32 poles; a lane walks its
+// share of the block row of the item's 1-D cell (block CSR of the 1-D matrix, cut at the end of the principal
+// sub-block of the pole's class) in a counted, unrolled loop, the sub-lanes are reduced with shuffles, and the K
+// outputs of a pole are added into the warp's PRIVATE copy of the CTA's output cells in shared memory (no races:
+// one item at a time per warp, distinct poles per lane).  One barrier, then the copies are summed into y.
+//   FlatCD table (ints, FLATCD stride per (multi-cell, direction)): {row begin, row end (derivative blocks),
+//   S, class p << 16 | 1-D cell q, then for level l = 0..p the multi-cell index of the item's first cell of level l}
+//   -- everything a record needs besides its block column, so the dependent-load chain is table -> column -> x.
+//   FlatMat: block records; the pre-squared Laplacian blocks S_p = (H[0:N',0:N'])^2 of the short classes
+//   (src/multidim_derivative.jl:71-79) have their own records per class: row q of class p is
+//   [rowptr[cls_row0[p] + q], rowend[cls_row0[p] + q]).
+//   Only items whose class lies in [pmin, pmax] are processed.
 // ------------------------------------------------------------------------------------------
-struct FlatCell {
+struct FlatCell {             // host-side description of a (multi-cell, direction): pole group, item, 1-D cell
     int group, r, q;
 };
 
 constexpr int FLAT_MAXD = 12;
+constexpr int FLATCD = 4 + ((MAXL + 1 + 3) & ~3);      // ints per (multi-cell, direction)
 
 struct FlatDirs {
-    const GroupDev* groups[FLAT_MAXD];
     double c[FLAT_MAXD];
     int A[FLAT_MAXD];
     int d[FLAT_MAXD];
@@ -1834,85 +1838,97 @@ struct FlatDirs {
 };
 
 struct FlatMat {
-    const int* rowptr;
+    const int* rowptr;        // squared blocks only (sq != 0)
+    const int* rowend;
     const int* col;
     const double* val;
     int KK2;
+    int sq;
     int cls_row0[MAXL + 1];
 };
 
-constexpr int FLAT_THREADS = 128;
+constexpr int FLAT_THREADS = 256;
+constexpr int FLAT_WARPS = FLAT_THREADS / 32;
 
 template <int K>
 __global__ void __launch_bounds__(FLAT_THREADS)
 sweep_flat_kernel(const double* __restrict__ X, double* __restrict__ Y, double beta, const FlatDirs fd,
-                  const FlatCell* __restrict__ cells, int D, int ncells, int cpc, const FlatMat M, int KD, int KDp,
-                  int PI, int G, int pmin, int pmax) {
-    extern __shared__ __align__(16) double acc_s[];          // cpc * KDp
-    const int tid = threadIdx.x, nth = blockDim.x;
+                  const int* __restrict__ celltab, int D, int ncells, int cpc, const FlatMat M, int KD, int KDp,
+                  int PI, int PIp, int RS, int pmin, int pmax) {
+    extern __shared__ __align__(16) double acc_s[];          // FLAT_WARPS private copies of cpc * KDp outputs
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c0 = blockIdx.x * cpc;
     const int nc = min(cpc, ncells - c0);
-    for (int i = tid; i < nc * KDp; i += nth) acc_s[i] = 0.0;
+    const int slab = cpc * KDp;
+    for (int i = tid; i < FLAT_WARPS * slab; i += FLAT_THREADS) acc_s[i] = 0.0;
     __syncthreads();
-    const int g = tid & (G - 1), ugrp = tid / G, ngrp = nth / G;
-    const int nunits = nc * PI;
-    for (int di = 0; di < fd.ndir; ++di) {
+    double* mine = acc_s + warp * slab;
+    const int jl = lane & (PIp - 1), sub = lane / PIp, G = 32 / PIp;     // pole inside the chunk, record sub-lane
+    const int nch = (PI + PIp - 1) / PIp;
+    const int nitems = fd.ndir * nc * nch * RS;
+    for (int it = warp; it < nitems; it += FLAT_WARPS) {      // warp-uniform control flow throughout
+        int t = it;
+        const int rsl = t % RS; t /= RS;
+        const int ch = t % nch; t /= nch;
+        const int cl = t % nc;
+        const int di = t / nc;
         const int A = fd.A[di], dd = fd.d[di];
-        const double cd = fd.c[di];
-        const GroupDev* __restrict__ groups = fd.groups[di];
-        for (int u0 = 0; u0 < nunits; u0 += ngrp) {          // uniform trip count: every lane reaches the shuffles
-            const int u = u0 + ugrp;
-            double acc[K];
-#pragma unroll
-            for (int m = 0; m < K; ++m) acc[m] = 0.0;
-            int cl = 0, po = 0;
-            bool live = false;
-            if (u < nunits) {
-                cl = u / PI;
-                const int j = u - cl * PI;
-                const int b = j / A, a = j - b * A;
-                po = a + K * A * b;
-                const FlatCell fc = cells[(size_t)(c0 + cl) * D + dd];
-                const GroupDev* gr = groups + fc.group;
-                const int p = gr->p;
-                live = p >= pmin && p <= pmax;
-                if (live) {
-                    const int NQ = 1 << p, S = gr->S;
-                    const int lo = fc.r % S, hi = fc.r / S;
-                    const int rb = M.cls_row0[p] + fc.q;
-                    const int r1 = __ldg(M.rowptr + rb + 1);
-                    for (int rec = __ldg(M.rowptr + rb) + g; rec < r1; rec += G) {
-                        const int qc = __ldg(M.col + rec);
-                        if (qc >= NQ) break;                 // block columns ascend: the rest lies outside the sub-block
-                        int ld, cdv, Cd;
-                        q_decode(qc, ld, cdv, Cd);
-                        const double* xv = X + gr->base[ld] + (long long)KDp * (lo + (long long)S * (cdv + (long long)Cd * hi)) + po;
-                        const double* hv = M.val + (size_t)rec * M.KK2;
-                        double xr[K];
-#pragma unroll
-                        for (int mi = 0; mi < K; ++mi) xr[mi] = xv[A * mi];
-#pragma unroll
-                        for (int mo = 0; mo < K; ++mo)
-#pragma unroll
-                            for (int mi = 0; mi < K; ++mi) acc[mo] = fma(__ldg(hv + mo * K + mi), xr[mi], acc[mo]);
-                    }
-                }
-            }
-            __syncwarp();
-            for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-                for (int m = 0; m < K; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
-            }
-            if (live && g == 0) {
-#pragma unroll
-                for (int m = 0; m < K; ++m) acc_s[cl * KDp + po + A * m] += cd * acc[m];
-            }
+        const int* __restrict__ cdp = celltab + ((size_t)(c0 + cl) * D + dd) * FLATCD;
+        const int pq = __ldg(cdp + 3);
+        const int p = pq >> 16;
+        if (p < pmin || p > pmax) continue;
+        int rbeg = __ldg(cdp), rend = __ldg(cdp + 1);
+        const int S = __ldg(cdp + 2);
+        if (M.sq) {
+            const int rb = M.cls_row0[p] + (pq & 0xffff);
+            rbeg = __ldg(M.rowptr + rb);
+            rend = __ldg(M.rowend + rb);
         }
-        __syncthreads();
+        const int j = ch * PIp + jl;
+        const bool valid = j < PI;
+        const int jj = valid ? j : 0;
+        const int b = jj / A, a = jj - b * A;
+        const int po = a + K * A * b;
+        double acc[K];
+#pragma unroll
+        for (int m = 0; m < K; ++m) acc[m] = 0.0;
+        // counted loop (no data-dependent exit): the gathers of the unrolled iterations are in flight together
+#pragma unroll 4
+        for (int rec = rbeg + rsl * G + sub; rec < rend; rec += G * RS) {
+            const int qc = __ldg(M.col + rec);
+            int ld, cdv, Cd;
+            q_decode(qc, ld, cdv, Cd);
+            const long long cell = (long long)__ldg(cdp + 4 + ld) + (long long)S * cdv;
+            const double* xv = X + cell * KDp + po;
+            const double* hv = M.val + (size_t)rec * M.KK2;
+            double xr[K];
+#pragma unroll
+            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[A * mi];
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(__ldg(hv + mo * K + mi), xr[mi], acc[mo]);
+        }
+        for (int o = PIp; o < 32; o <<= 1) {
+#pragma unroll
+            for (int m = 0; m < K; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+        }
+        if (valid && sub == 0) {
+            const double cd = fd.c[di];
+#pragma unroll
+            for (int m = 0; m < K; ++m) mine[cl * KDp + po + A * m] += cd * acc[m];
+        }
+        __syncwarp();                    // the next item of this warp may touch the same outputs from other lanes
     }
+    __syncthreads();
     double* yo = Y + (size_t)c0 * KDp;
-    for (int i = tid; i < nc * KDp; i += nth) {
-        if (i % KDp < KD) yo[i] = beta == 0.0 ? acc_s[i] : fma(beta, yo[i], acc_s[i]);
+    for (int i = tid; i < nc * KDp; i += FLAT_THREADS) {
+        if (i % KDp < KD) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < FLAT_WARPS; ++w) sum += acc_s[w * slab + i];
+            yo[i] = beta == 0.0 ? sum : fma(beta, yo[i], sum);
+        }
     }
 }
 

@@ -101,9 +101,11 @@ int gsg_vlasov_create(gsg_plan* plan, gsg_csr* m2n, gsg_csr* n2p, gsg_csr* p2n, 
         gsg::tensor_construct(S, arr.data(), vm.data());
         GSG_TRY(V->v_point[i].resize(N));
         GSG_TRY(V->F_point[i].resize(N));
-        GSG_CUDA(cudaMemcpy(V->r1.p, vm.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        // everything on the plan's (non-blocking) stream, and waited for before vm / r1 are reused by the next dimension
+        GSG_CUDA(cudaMemcpyAsync(V->r1.p, vm.data(), N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
         GSG_TRY(gsg_csr_apply_dev(m2n, V->r1.p, V->r2.p, plan->stream));
         GSG_TRY(gsg_csr_apply_dev(n2p, V->r2.p, V->v_point[i].p, plan->stream));               // v_point = n2p * (m2n * v)
+        GSG_CUDA(cudaStreamSynchronize(plan->stream));
         if (!F_point[i]) return fail(GSG_ERR_ARG, "null F_point vector");
         GSG_CUDA(cudaMemcpyAsync(V->F_point[i].p, F_point[i], N * sizeof(double), cudaMemcpyHostToDevice, plan->stream));
     }

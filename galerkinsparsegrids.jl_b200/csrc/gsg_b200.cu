@@ -1223,7 +1223,7 @@ constexpr int64_t FLAT_AUTO_MAX = 6000000;       // automatic mode: N * D up to 
 
 bool flat_supported(const gsg_plan& pl) {
     return pl.S.k >= 1 && pl.S.k <= 5 && pl.S.D <= FLAT_MAXD && pl.part_bits == 0 && pl.S.ncells_total < 0x7fffffffLL &&
-           (size_t)FLAT_WARPS * pl.S.kDp * sizeof(double) <= 48 * 1024 && pl.S.n <= 15;
+           (size_t)FLAT_WARPS * pl.S.kDp * sizeof(double) + (size_t)pl.S.D * pl.S.kD * sizeof(int) <= 96 * 1024 && pl.S.n <= 15;
 }
 
 bool flat_on(const gsg_plan& pl) {
@@ -1269,19 +1269,29 @@ int launch_flat_k(gsg_plan& pl, const FlatDirs& fd, const FlatMat& M, const doub
         while (PIp < PI && PIp < 32) PIp <<= 1;
         const int nch = (PI + PIp - 1) / PIp;
         const int nd = std::max(1, fd.ndir);
-        // cells per CTA: one when a cell fills half a warp's lanes with poles, else enough for ~8 items; record slices so
-        // that a CTA has ~16 items for its 8 warps (long rows -- the coarse cells -- are cut into more pieces)
-        int cpc = PI >= 16 ? 1 : std::max(1, std::min(8, (8 + nd * nch - 1) / (nd * nch)));
-        while (cpc > 1 && (size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double) > 48 * 1024) --cpc;
-        const int RS = std::max(1, std::min(8, 16 / (nd * nch * cpc)));
+        // one multi-cell per CTA (GSG_FLAT_CPC: more, for experiments): the kernel cuts long rows -- the coarse cells --
+        // into record slices that the CTA's 8 warps share
+        static const int cpc_env = getenv("GSG_FLAT_CPC") ? atoi(getenv("GSG_FLAT_CPC")) : 1;
+        int cpc = std::max(1, std::min(8, cpc_env));
+        while (cpc > 1 && ((size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double) > 40 * 1024 || cpc * nd > 32)) --cpc;
         const int ncells = (int)pl.S.ncells_total;
         const int grid = (ncells + cpc - 1) / cpc;
-        const size_t smem = (size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double);
-        auto kern = sweep_flat_kernel<K>;       // <= 48 KB of shared memory (flat_supported): the default carve-out keeps the L1 for the gathers
+        const size_t smem = (size_t)FLAT_WARPS * cpc * pl.S.kDp * sizeof(double) + (size_t)nd * PI * sizeof(int);
+        auto kern = sweep_flat_kernel<K>;       // default carve-out (the L1 serves the gathers); opt in above 48 KB only (k^D ~ 700)
+        if (smem > 48 * 1024) {
+            static std::mutex mu;
+            static std::map<std::pair<const void*, int>, size_t> done;
+            std::lock_guard<std::mutex> lock(mu);
+            size_t& have = done[std::make_pair(reinterpret_cast<const void*>(kern), pl.device)];
+            if (smem > have) {
+                GSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                have = smem;
+            }
+        }
         const bool prof = pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size());
         if (prof) GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].first, pl.stream));
         kern<<<grid, FLAT_THREADS, smem, pl.stream>>>(x, y, beta, fd, pl.flat_cd.p, pl.S.D, ncells, cpc, M, (int)pl.S.kD,
-                                                       (int)pl.S.kDp, PI, PIp, RS, pmin, pmax);
+                                                       (int)pl.S.kDp, PI, PIp, pmin, pmax);
         if (prof) {
             GSG_CUDA(cudaEventRecord(pl.prof_ev[pl.prof_used].second, pl.stream));
             ++pl.prof_used;

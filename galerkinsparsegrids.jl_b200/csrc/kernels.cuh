@@ -1850,80 +1850,119 @@ struct FlatMat {
 constexpr int FLAT_THREADS = 256;
 constexpr int FLAT_WARPS = FLAT_THREADS / 32;
 
+constexpr int FLAT_U = 4;          // records per sub-lane and item: their gathers are in flight together
+
 template <int K>
 __global__ void __launch_bounds__(FLAT_THREADS)
 sweep_flat_kernel(const double* __restrict__ X, double* __restrict__ Y, double beta, const FlatDirs fd,
                   const int* __restrict__ celltab, int D, int ncells, int cpc, const FlatMat M, int KD, int KDp,
-                  int PI, int PIp, int RS, int pmin, int pmax) {
-    extern __shared__ __align__(16) double acc_s[];          // FLAT_WARPS private copies of cpc * KDp outputs
+                  int PI, int PIp, int pmin, int pmax) {
+    extern __shared__ __align__(16) double acc_s[];          // FLAT_WARPS private copies of cpc * KDp outputs, then po_s
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c0 = blockIdx.x * cpc;
     const int nc = min(cpc, ncells - c0);
     const int slab = cpc * KDp;
-    for (int i = tid; i < FLAT_WARPS * slab; i += FLAT_THREADS) acc_s[i] = 0.0;
-    __syncthreads();
     double* mine = acc_s + warp * slab;
+    int* po_s = reinterpret_cast<int*>(acc_s + FLAT_WARPS * slab);      // [ndir][PI]: in-cell offset of pole j along d
+    for (int i = lane; i < slab; i += 32) mine[i] = 0.0;
+    for (int i = tid; i < fd.ndir * PI; i += FLAT_THREADS) {
+        const int di = i / PI, j = i - di * PI, A = fd.A[di];
+        const int b = j / A;
+        po_s[i] = (j - b * A) + K * A * b;
+    }
+    // longest block row among this CTA's (cell, direction) pairs (nc * ndir <= 32): coarse cells (rows of up to 2^n
+    // records) are cut into more record slices, so that an item is ONE batch of FLAT_U records per sub-lane and the
+    // CTA's warps share a long row.  The slice count is a power of two (item decoding by shifts).
+    int len = 0;
+    if (lane < nc * fd.ndir) {
+        const int* cdp = celltab + ((size_t)(c0 + lane % nc) * D + fd.d[lane / nc]) * FLATCD;
+        len = __ldg(cdp + 1) - __ldg(cdp);
+    }
+    len = __reduce_max_sync(0xffffffffu, len);
     const int jl = lane & (PIp - 1), sub = lane / PIp, G = 32 / PIp;     // pole inside the chunk, record sub-lane
     const int nch = (PI + PIp - 1) / PIp;
-    const int nitems = fd.ndir * nc * nch * RS;
+    int rs_log = 0;
+    while (rs_log < 6 && ((G * FLAT_U) << rs_log) < len) ++rs_log;
+    const int RS = 1 << rs_log;
+    const int per_dir = nc * nch;
+    const int nitems = fd.ndir * per_dir * RS;
+    __syncthreads();
     for (int it = warp; it < nitems; it += FLAT_WARPS) {      // warp-uniform control flow throughout
-        int t = it;
-        const int rsl = t % RS; t /= RS;
-        const int ch = t % nch; t /= nch;
-        const int cl = t % nc;
-        const int di = t / nc;
+        const int rsl = it & (RS - 1);
+        int t = it >> rs_log;
+        const int di = t / per_dir;
+        t -= di * per_dir;
+        const int cl = nc == 1 ? 0 : t / nch;
+        const int ch = t - cl * nch;
         const int A = fd.A[di], dd = fd.d[di];
-        const int* __restrict__ cdp = celltab + ((size_t)(c0 + cl) * D + dd) * FLATCD;
-        const int pq = __ldg(cdp + 3);
+        // the item's table record, one coalesced load: lanes 0..3 = {row begin, row end, S, p << 16 | q}, lane 4 + l =
+        // multi-cell index of the item's first cell of level l (fetched with shuffles: no dependent table load later)
+        const int tv = lane < FLATCD ? __ldg(celltab + ((size_t)(c0 + cl) * D + dd) * FLATCD + lane) : 0;
+        const int pq = __shfl_sync(0xffffffffu, tv, 3);
         const int p = pq >> 16;
         if (p < pmin || p > pmax) continue;
-        int rbeg = __ldg(cdp), rend = __ldg(cdp + 1);
-        const int S = __ldg(cdp + 2);
+        int rbeg = __shfl_sync(0xffffffffu, tv, 0), rend = __shfl_sync(0xffffffffu, tv, 1);
+        const int S = __shfl_sync(0xffffffffu, tv, 2);
         if (M.sq) {
             const int rb = M.cls_row0[p] + (pq & 0xffff);
             rbeg = __ldg(M.rowptr + rb);
             rend = __ldg(M.rowend + rb);
         }
+        const int step = G << rs_log;
+        int rec = rbeg + rsl * G + sub;
+        if (__all_sync(0xffffffffu, rec >= rend)) continue;          // empty slice
         const int j = ch * PIp + jl;
         const bool valid = j < PI;
-        const int jj = valid ? j : 0;
-        const int b = jj / A, a = jj - b * A;
-        const int po = a + K * A * b;
-        double acc[K];
+        const int po = po_s[di * PI + (valid ? j : 0)];
+        double r[K];
 #pragma unroll
-        for (int m = 0; m < K; ++m) acc[m] = 0.0;
-        // counted loop (no data-dependent exit): the gathers of the unrolled iterations are in flight together
-#pragma unroll 4
-        for (int rec = rbeg + rsl * G + sub; rec < rend; rec += G * RS) {
-            const int qc = __ldg(M.col + rec);
-            int ld, cdv, Cd;
-            q_decode(qc, ld, cdv, Cd);
-            const long long cell = (long long)__ldg(cdp + 4 + ld) + (long long)S * cdv;
-            const double* xv = X + cell * KDp + po;
-            const double* hv = M.val + (size_t)rec * M.KK2;
-            double xr[K];
+        for (int m = 0; m < K; ++m) r[m] = 0.0;
+        // FLAT_U records at a time: columns and block values first (they depend on the record only), then the x gathers
+        for (; __any_sync(0xffffffffu, rec < rend); rec += FLAT_U * step) {
+            double xr[FLAT_U][K], hv[FLAT_U][K * K];
+            int qc[FLAT_U];
+            bool on[FLAT_U];
 #pragma unroll
-            for (int mi = 0; mi < K; ++mi) xr[mi] = xv[A * mi];
+            for (int u = 0; u < FLAT_U; ++u) {
+                const int r = rec + u * step;
+                on[u] = r < rend;
+                const int rr = on[u] ? r : rbeg;
+                qc[u] = __ldg(M.col + rr);
+                const double* hp = M.val + (size_t)rr * M.KK2;
 #pragma unroll
-            for (int mo = 0; mo < K; ++mo)
+                for (int e = 0; e < K * K; ++e) hv[u][e] = __ldg(hp + e);
+            }
 #pragma unroll
-                for (int mi = 0; mi < K; ++mi) acc[mo] = fma(__ldg(hv + mo * K + mi), xr[mi], acc[mo]);
+            for (int u = 0; u < FLAT_U; ++u) {
+                int ld, cdv, Cd;
+                q_decode(qc[u], ld, cdv, Cd);
+                const long long cell = (long long)__shfl_sync(0xffffffffu, tv, 4 + ld) + (long long)S * cdv;
+                const double* xv = X + cell * KDp + po;
+#pragma unroll
+                for (int mi = 0; mi < K; ++mi) xr[u][mi] = on[u] ? xv[A * mi] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < FLAT_U; ++u)
+#pragma unroll
+                for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                    for (int mi = 0; mi < K; ++mi) r[mo] = fma(hv[u][mo * K + mi], xr[u][mi], r[mo]);
         }
         for (int o = PIp; o < 32; o <<= 1) {
 #pragma unroll
-            for (int m = 0; m < K; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+            for (int m = 0; m < K; ++m) r[m] += __shfl_xor_sync(0xffffffffu, r[m], o);
         }
         if (valid && sub == 0) {
             const double cd = fd.c[di];
 #pragma unroll
-            for (int m = 0; m < K; ++m) mine[cl * KDp + po + A * m] += cd * acc[m];
+            for (int m = 0; m < K; ++m) mine[cl * KDp + po + A * m] += cd * r[m];
         }
         __syncwarp();                    // the next item of this warp may touch the same outputs from other lanes
     }
     __syncthreads();
     double* yo = Y + (size_t)c0 * KDp;
     for (int i = tid; i < nc * KDp; i += FLAT_THREADS) {
-        if (i % KDp < KD) {
+        if (nc > 1 ? (i % KDp < KD) : (i < KD)) {
             double sum = 0.0;
 #pragma unroll
             for (int w = 0; w < FLAT_WARPS; ++w) sum += acc_s[w * slab + i];

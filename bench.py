@@ -398,6 +398,8 @@ def main():
 
     plan = g.Plan(D, k, n, device=local_rank)
     N = plan.size
+    if rank == 0 and os.environ.get("GSG_DESCRIBE"):
+        print(plan.describe(), file=sys.stderr, flush=True)
     v1d = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
     u0 = g.tensor_construct(D, k, n, [v1d] * D)                  # host copy for the end-to-end (host buffer) leg
     stream = torch.cuda.Stream(device=device)

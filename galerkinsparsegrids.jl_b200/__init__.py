@@ -86,6 +86,20 @@ def flat_tables(D: int, k: int, n: int, d: int, scheme: str = "sparse"):
     return groups, cells
 
 
+def rowtile_program(D: int, k: int, n: int, p: int, budget_bytes: int = 112 * 1024, nrg: int = 2):
+    """CPU-side copy of the row-tile kernel's tile program for pole class p (library's own H(k, n), multi-cells of
+    k^D doubles): dict with tiles [nt, 48] int32, rows [nr, 4] int32, rec_h [nrec, k, k], rec_slot [nrec]."""
+    cnt = (C.c_int64 * 3)()
+    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, None, None, None, None, cnt))
+    tiles = np.zeros((cnt[0], 48), dtype=np.int32)
+    rows = np.zeros((cnt[1], 4), dtype=np.int32)
+    rec_h = np.zeros((cnt[2], k, k))
+    rec_slot = np.zeros(cnt[2], dtype=np.int32)
+    vp_ = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, vp_(tiles), vp_(rows), vp_(rec_h), vp_(rec_slot), cnt))
+    return {"tiles": tiles, "rows": rows, "rec_h": rec_h, "rec_slot": rec_slot}
+
+
 def get_size(D: int, k: int, n: int, scheme: str = "sparse") -> int:
     """get_size(Val(D), k, n, Val(scheme)) -- src/dg_vmethods.jl:35-45."""
     out = C.c_int64()
@@ -346,6 +360,12 @@ class Plan:
     def set_flat(self, mode: int) -> None:
         """0 = tiled class kernels, 1 = flat kernel (one launch per right-hand side), 2 = automatic (default)."""
         check(lib.gsg_plan_set_flat(self._h, int(mode)))
+
+    def describe(self) -> str:
+        """which kernel serves which pole classes, per direction"""
+        buf = C.create_string_buffer(8192)
+        check(lib.gsg_plan_describe(self._h, buf, 8192))
+        return buf.value.decode()
 
     @property
     def flat_active(self) -> bool:

@@ -106,7 +106,7 @@ constexpr size_t SMEM_OPTIN_MAX = 227 * 1024;
 constexpr int SHORT_TILE_DOUBLES = 4096;
 constexpr int TMA_STAGE_TARGET_DOUBLES = 5840;
 
-enum class Kind { SHORT_TMA, LONG, LONG2, CONSTH, GENERIC };   // LONG: transient tag while a class is being placed
+enum class Kind { SHORT_TMA, LONG, LONG2, CONSTH, GENERIC, ROWTILE };   // LONG: transient tag while a class is being placed
 
 struct SweepClass {          // one launch of a sweep
     int p = 0;               // pole length class (SHORT_TMA: the largest short class it holds)
@@ -123,6 +123,8 @@ struct SweepClass {          // one launch of a sweep
     DevBuf<TileDev> tiles;
     DevBuf<TileS> stiles;
     DevBuf<TileS2> s2tiles;     // second-generation streaming kernel
+    DevBuf<RTWork> rtwork;      // row-tile kernel: (item, tile) work list, heaviest tiles first
+    DevBuf<int> rtzero;         // ... and the multi-cells that receive partial sums (zeroed before a beta = 0 sweep)
     bool stream2 = false;
     ShortParams sprm{};
     int ntiles = 0;
@@ -135,10 +137,14 @@ struct Direction {
     std::vector<GroupDev> groups_h;
     DevBuf<CellOfs> celltab;     // register-tiled long kernel: per group, one entry per 1-D cell
     DevBuf<int> offtab;          // in-cell offset of pole j: a + K*A*b
+    DevBuf<int> rt_offtab;       // row-tile kernel: the same offsets in an order whose consecutive poles are free of
+                                 // shared-memory bank conflicts (b fastest while A < 16: the stride K*A is odd)
     std::vector<SweepClass> classes;
 };
 
 }  // namespace
+
+#include "rowtile.inl"
 
 struct gsg_plan {
     gsg::IndexSet S;
@@ -203,6 +209,15 @@ struct gsg_plan {
     long long* dbg = nullptr;     // optional clock-stamp buffer (gsg_debug_stamps)
     DevBuf<long long> dbgbuf;
 
+    // row-tile kernel for the long-pole classes (rowtile.inl): tile programs of the classes rt_pmin..n
+    bool rt_on = false;
+    int rt_pmin = 0, rt_C = 1, rt_PW = 1, rt_RG = 1;
+    size_t rt_smem = 0;
+    RTProgram rt_prog;
+    DevBuf<RTTile> rt_tiles;
+    DevBuf<RTRow> rt_rows;
+    DevBuf<unsigned char> rt_recs;
+
     // flat path (kernels.cuh, sweep_flat_kernel): one launch per right-hand side for small index sets.
     // flat_mode: 0 = never, 1 = whenever supported, 2 = automatic (N * D <= FLAT_AUTO_MAX)
     int flat_mode = 2;
@@ -258,6 +273,68 @@ bool short_supported(int K, int p) {
 // ------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------
+// K x K block CSR (block columns ascending, blocks row-major, padded to KK2 doubles) of a dense N1 x N1 matrix with
+// the stored-block mask blk
+void block_csr_from_dense(const std::vector<double>& Hd, const std::vector<char>& blk, int64_t N1, int K, int NQ, int KK2,
+                          std::vector<int>& rowptr, std::vector<int>& col, std::vector<double>& val) {
+    rowptr.assign(NQ + 1, 0);
+    col.clear();
+    val.clear();
+    for (int q = 0; q < NQ; ++q) {
+        for (int qc = 0; qc < NQ; ++qc) {
+            if (!blk[(size_t)q * NQ + qc]) continue;
+            col.push_back(qc);
+            const size_t o = val.size();
+            val.resize(o + KK2, 0.0);
+            for (int mo = 0; mo < K; ++mo)
+                for (int mi = 0; mi < K; ++mi)
+                    val[o + mo * K + mi] = Hd[(size_t)(q * K + mo) * N1 + (qc * K + mi)];
+        }
+        rowptr[q + 1] = (int)col.size();
+    }
+}
+
+// Row-tile kernel for the long-pole classes: eligible when an item has enough poles to fill the lanes (k^(D-1) >= 64,
+// i.e. the big index sets: D = 6 / 5 at k = 3, D = 4 at k = 4, 5) and the program fits.  GSG_ROWTILE=0 turns it off
+// (the constant-bank / register-tiled kernels then serve those classes), GSG_RT_BUDGET_KB sets the shared-memory
+// budget of a tile (default 112 KB: two CTAs per SM).
+int build_rowtile_program(gsg_plan& P) {
+    P.rt_on = false;
+    const int K = P.S.k, n = P.S.n;
+    const int PI = (int)(P.S.kD / K);
+    const char* env = getenv("GSG_ROWTILE");
+    if (!env || atoi(env) == 0) return 0;                 // opt-in while it is being measured
+    if (K > 5 || PI < 64 || PI > 512) return 0;
+    int pmin = 0;
+    while (pmin <= n && short_supported(K, pmin)) ++pmin;
+    if (pmin > n) return 0;
+    size_t budget = 112 * 1024;
+    if (const char* e = getenv("GSG_RT_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
+    budget = std::min(budget, SMEM_OPTIN_MAX - 1024);
+    P.rt_C = PI > 96 ? 2 : 1;
+    if (const char* e = getenv("GSG_RT_C")) {
+        const int c = atoi(e);
+        if (c == 1 || c == 2 || (c == 4 && K <= 3)) P.rt_C = c;
+    }
+    P.rt_PW = (PI + 32 * P.rt_C - 1) / (32 * P.rt_C);
+    if (P.rt_PW > 8) return 0;
+    P.rt_RG = std::max(1, std::min(RT_MAXRG, 8 / P.rt_PW));
+    if (rt_build_program(P.h_rowptr, P.h_col, P.h_val, P.KK2, K, (int)P.S.kDp, n, pmin, budget, P.rt_RG, P.rt_prog) != 0) {
+        P.rt_prog = RTProgram();
+        return 0;                                         // no tiling fits: the other kernels serve these classes
+    }
+    size_t need = 0;
+    for (const RTTile& T : P.rt_prog.tiles)
+        need = std::max(need, (size_t)64 + (size_t)T.nx * P.S.kDp * 8 + (size_t)T.nrec * P.rt_prog.rec_bytes);
+    P.rt_smem = need;
+    GSG_TRY(P.rt_tiles.upload(P.rt_prog.tiles));
+    GSG_TRY(P.rt_rows.upload(P.rt_prog.rows));
+    GSG_TRY(P.rt_recs.upload(P.rt_prog.recs));
+    P.rt_pmin = pmin;
+    P.rt_on = true;
+    return 0;
+}
+
 int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
     const int K = P.S.k;
     const int n = P.S.n;
@@ -278,20 +355,9 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         }
     }
     P.KK2 = (K * K + 1) & ~1;
-    std::vector<int> rowptr(NQ + 1, 0), col;
+    std::vector<int> rowptr, col;
     std::vector<double> val;
-    for (int q = 0; q < NQ; ++q) {
-        for (int qc = 0; qc < NQ; ++qc) {
-            if (!blk[(size_t)q * NQ + qc]) continue;
-            col.push_back(qc);
-            const size_t o = val.size();
-            val.resize(o + P.KK2, 0.0);
-            for (int mo = 0; mo < K; ++mo)
-                for (int mi = 0; mi < K; ++mi)
-                    val[o + mo * K + mi] = Hd[(size_t)(q * K + mo) * N1 + (qc * K + mi)];
-        }
-        rowptr[q + 1] = (int)col.size();
-    }
+    block_csr_from_dense(Hd, blk, N1, K, NQ, P.KK2, rowptr, col, val);
     P.h_rowptr = rowptr;
     P.h_col = col;
     P.h_val = val;
@@ -387,6 +453,7 @@ int build_matrix(gsg_plan& P, int64_t Hn, const int64_t* colptr, const int64_t* 
         GSG_TRY(P.sq_col.upload(cl));
         GSG_TRY(P.sq_val.upload(vl));
     }
+    GSG_TRY(build_rowtile_program(P));
     return 0;
 }
 
@@ -612,12 +679,64 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         GSG_TRY(dir.offtab.upload(offtab));
     }
 
+    // ---- row-tile class: every long-pole class p >= rt_pmin in ONE launch, CTA = (item, tile of the class's program)
+    const bool rowtile = P.rt_on && tma_active;
+    if (rowtile) {
+        std::vector<int> ot(PI);
+        const int B = PI / dir.A;
+        static const bool plain = getenv("GSG_RT_PLAIN_ORDER") != nullptr;
+        for (int j = 0; j < PI; ++j) {
+            int a, b;
+            if (dir.A >= 16 || B == 1 || plain) { a = j % dir.A; b = j / dir.A; }
+            else { b = j % B; a = j / B; }
+            ot[j] = a + K * dir.A * b;
+        }
+        GSG_TRY(dir.rt_offtab.upload(ot));
+        SweepClass c;
+        c.kind = Kind::ROWTILE;
+        c.p = n;
+        std::vector<RTWork> work;
+        std::vector<int> zero;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const GroupDev& g = groups[gi];
+            if (g.p < P.rt_pmin) continue;
+            const int NQ = 1 << g.p;
+            const int ctab = (int)celltab.size();
+            const long long KS = (long long)KDp * g.S;
+            for (int q = 0; q < NQ; ++q) {
+                const int ld = q == 0 ? 0 : 32 - __builtin_clz((unsigned)q);
+                const int cd = q == 0 ? 0 : q - (1 << (ld - 1));
+                const int Cd = ld <= 1 ? 1 : 1 << (ld - 1);
+                celltab.push_back(CellOfs{g.base[ld] + KS * cd, KS * Cd});
+            }
+            for (int r = 0; r < g.nitems; ++r) {
+                const int lo = r % g.S, hi = r / g.S;
+                for (int t = 0; t < P.rt_prog.cls_count[g.p]; ++t) work.push_back(RTWork{ctab, lo, hi, P.rt_prog.cls_first[g.p] + t});
+                for (int q : P.rt_prog.cls_partial_q[g.p]) {
+                    const CellOfs& co = celltab[ctab + q];
+                    zero.push_back((int)((co.bq + (long long)KDp * lo + co.kc * hi) / KDp));
+                }
+            }
+        }
+        if (!work.empty()) {
+            std::stable_sort(work.begin(), work.end(), [&](const RTWork& a, const RTWork& b) {
+                return P.rt_prog.tiles[a.tile].nrec > P.rt_prog.tiles[b.tile].nrec;
+            });
+            c.ntiles = (int)work.size();
+            c.smem = P.rt_smem;
+            GSG_TRY(c.rtwork.upload(work));
+            GSG_TRY(c.rtzero.upload(zero));
+            dir.classes.push_back(std::move(c));
+        }
+    }
+
     for (int p = 0; p <= n; ++p) {
         SweepClass c;
         c.p = p;
         const int NQ = 1 << p, NP = K * NQ;
         const int REC = (K * K * 8 + 8 + 15) & ~15;
         if (short_supported(K, p) && tma_active) continue;        // served by the streaming class above
+        if (rowtile && p >= P.rt_pmin) continue;                  // served by the row-tile class above
         // register-tiled / constant-bank kernels for the long classes of k <= 5; everything else (k > 5, short
         // classes whose stage does not fit shared memory) goes to the generic block-CSR kernel
         c.kind = (K <= 5 && !short_supported(K, p)) ? Kind::LONG : Kind::GENERIC;
@@ -1189,6 +1308,34 @@ int launch_generic_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
     return launch_check("sweep_generic", K, c);
 }
 
+template <int K>
+int launch_rowtile_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const SweepClass& c, const double* x,
+                     double* y, double alpha, double beta) {
+    if constexpr (K >= 1 && K <= 5) {
+        if (c.ntiles == 0) return 0;
+        const int PI = (int)pl.S.kD / K, KDp = (int)pl.S.kDp;
+        if (beta == 0.0 && c.rtzero.n > 0) {      // rows that only receive partial sums start from zero
+            const int nz = (int)c.rtzero.n;
+            zero_cells_kernel<<<std::min(nz, pl.sm_count * 8), 128, 0, st>>>(y, c.rtzero.p, nz, KDp);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        const int threads = 32 * pl.rt_PW * pl.rt_RG;
+        auto go = [&](auto kern) -> int {
+            static thread_local size_t configured = 0;
+            GSG_TRY(ensure_smem(kern, c.smem, configured));
+            kern<<<c.ntiles, threads, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.rt_offtab.p, c.rtwork.p,
+                                                     pl.rt_tiles.p, pl.rt_rows.p, pl.rt_recs.p, KDp, dir.A, PI, pl.rt_PW, pl.rt_RG);
+            return 0;
+        };
+        if (pl.rt_C == 4) { if constexpr (K <= 3) GSG_TRY(go(sweep_rowtile_kernel<K, 4>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 4 for k > 3"); }
+        else if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2>));
+        else GSG_TRY(go(sweep_rowtile_kernel<K, 1>));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return launch_check("sweep_rowtile", K, c);
+    }
+    return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile kernel not instantiated");
+}
+
 #define GSG_K_SWITCH(FN, ...)                       \
     switch (K) {                                    \
         case 1: return FN<1>(__VA_ARGS__);          \
@@ -1206,6 +1353,7 @@ int launch_class(gsg_plan& pl, cudaStream_t st, const Direction& dir, const Swee
         case Kind::SHORT_TMA: GSG_K_SWITCH(launch_short_tma, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::LONG2: GSG_K_SWITCH(launch_long2_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::CONSTH: return launch_consth(pl, st, dir, c, x, y, alpha, beta);
+        case Kind::ROWTILE: GSG_K_SWITCH(launch_rowtile_k, pl, st, dir, c, x, y, alpha, beta); break;
         case Kind::GENERIC:
             GSG_K_SWITCH(launch_generic_k, pl, st, dir, c, x, y, alpha, beta);
             return launch_generic_k<0>(pl, st, dir, c, x, y, alpha, beta);
@@ -2026,6 +2174,29 @@ int gsg_plan_flat_active(const gsg_plan* plan, int* active_out) {
     return 0;
 }
 
+// one line per direction: the launches of a sweep as "kind(p, tiles)" -- which kernel serves which pole classes
+int gsg_plan_describe(const gsg_plan* plan, char* buf, size_t buflen) {
+    if (!plan || !buf || buflen == 0) return fail(GSG_ERR_ARG, "null pointer");
+    static const char* const names[] = {"stream", "long", "long2", "consth", "generic", "rowtile"};
+    std::string out;
+    char tmp[160];
+    snprintf(tmp, sizeof tmp, "D=%d k=%d n=%d N=%lld flat=%d pair_np=%d rowtile=%d(pmin=%d C=%d PW=%d RG=%d smem=%zu tiles=%zu)\n",
+             plan->S.D, plan->S.k, plan->S.n, (long long)plan->S.N, flat_on(*plan) ? 1 : 0, plan->pair_np, plan->rt_on ? 1 : 0,
+             plan->rt_pmin, plan->rt_C, plan->rt_PW, plan->rt_RG, plan->rt_smem, plan->rt_prog.tiles.size());
+    out += tmp;
+    for (size_t d = 0; d < plan->dirs.size(); ++d) {
+        snprintf(tmp, sizeof tmp, "d=%zu:", d + 1);
+        out += tmp;
+        for (const SweepClass& c : plan->dirs[d].classes) {
+            snprintf(tmp, sizeof tmp, " %s(p=%d,%d)", names[(int)c.kind], c.p, c.ntiles);
+            out += tmp;
+        }
+        out += "\n";
+    }
+    snprintf(buf, buflen, "%s", out.c_str());
+    return 0;
+}
+
 int gsg_plan_set_flat(gsg_plan* plan, int mode) {
     if (!plan || mode < 0 || mode > 2) return fail(GSG_ERR_ARG, "flat mode must be 0 (tiled), 1 (flat) or 2 (automatic)");
     plan->flat_mode = mode;
@@ -2056,6 +2227,62 @@ int gsg_debug_flat_tables(int D, int k, int n, int scheme, int d, int64_t* group
             cells_out[3 * c] = fc.group; cells_out[3 * c + 1] = fc.r; cells_out[3 * c + 2] = fc.q;
         }
     }
+    return 0;
+}
+
+// CPU-side check of the row-tile program (no device needed): the tile program of pole class p for the library's own
+// H = periodic_DLF_matrix(k, n), multi-cells of k^D doubles.  Two-call pattern: NULL outputs return the counts
+// {tiles, rows, records}.  tiles_out: (8 + 40) int32 per tile {nx, rec0, nrec, row0, rg_end[4], xq[40]}; rows_out:
+// 4 int32 per row {q, rb, re, partial}; rec_h_out: k*k doubles per record (row-major); rec_slot_out: x slot per record.
+int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out, int32_t* rows_out,
+                              double* rec_h_out, int32_t* rec_slot_out, int64_t* counts_out) {
+    GSG_TRY(check_dkn(D, k, n, 0));
+    if (p < 0 || p > n || !counts_out) return fail(GSG_ERR_ARG, "bad argument");
+    const gsg::Csc H = gsg::periodic_hier_DLF_matrix(k, n);
+    const int64_t N1 = H.n;
+    const int NQ = 1 << n;
+    std::vector<double> Hd((size_t)N1 * N1, 0.0);
+    std::vector<char> blk((size_t)NQ * NQ, 0);
+    for (int64_t j = 0; j < N1; ++j)
+        for (int64_t pp = H.colptr[j]; pp < H.colptr[j + 1]; ++pp) {
+            const int64_t i = H.rowval[pp];
+            Hd[(size_t)i * N1 + j] += H.nzval[pp];
+            blk[(size_t)(i / k) * NQ + (j / k)] = 1;
+        }
+    const int KK2 = (k * k + 1) & ~1;
+    std::vector<int> rowptr, col;
+    std::vector<double> val;
+    block_csr_from_dense(Hd, blk, N1, k, NQ, KK2, rowptr, col, val);
+    int64_t kD = 1;
+    for (int i = 0; i < D; ++i) kD *= k;
+    const int KDp = (int)((kD + 1) & ~int64_t(1));
+    RTProgram prog;
+    GSG_TRY(rt_build_program(rowptr, col, val, KK2, k, KDp, p, p, (size_t)budget_bytes, nrg, prog));
+    const int64_t nrec = (int64_t)(prog.recs.size() / prog.rec_bytes);
+    counts_out[0] = (int64_t)prog.tiles.size();
+    counts_out[1] = (int64_t)prog.rows.size();
+    counts_out[2] = nrec;
+    if (tiles_out)
+        for (size_t t = 0; t < prog.tiles.size(); ++t) {
+            const RTTile& T = prog.tiles[t];
+            int32_t* o = tiles_out + t * (8 + RT_MAXX);
+            o[0] = T.nx; o[1] = T.rec0; o[2] = T.nrec; o[3] = T.row0;
+            for (int g = 0; g < RT_MAXRG; ++g) o[4 + g] = T.rg_end[g];
+            for (int i = 0; i < RT_MAXX; ++i) o[8 + i] = T.xq[i];
+        }
+    if (rows_out)
+        for (size_t r = 0; r < prog.rows.size(); ++r) {
+            rows_out[4 * r] = prog.rows[r].q; rows_out[4 * r + 1] = prog.rows[r].rb;
+            rows_out[4 * r + 2] = prog.rows[r].re; rows_out[4 * r + 3] = prog.rows[r].partial;
+        }
+    if (rec_h_out && rec_slot_out)
+        for (int64_t r = 0; r < nrec; ++r) {
+            const unsigned char* rec = prog.recs.data() + (size_t)r * prog.rec_bytes;
+            std::memcpy(rec_h_out + r * k * k, rec, (size_t)k * k * 8);
+            int meta[2];
+            std::memcpy(meta, rec + (size_t)k * k * 8, 8);
+            rec_slot_out[r] = meta[0] / (KDp * 8);
+        }
     return 0;
 }
 

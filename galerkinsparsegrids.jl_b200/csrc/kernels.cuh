@@ -1270,6 +1270,148 @@ sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Long poles, ROW-TILE kernel (N' >= 48 when an item has >= 64 poles; rowtile.inl builds the tile programs).
+// Unit of data movement = the whole multi-cell (all k^(D-1) poles of an item for one 1-D cell: ONE contiguous,
+// 16-byte aligned run), so the x tile is staged with a handful of TMA bulk copies (UBLKCP) instead of 8-byte
+// gathers, lanes = poles (C per lane), and a CTA = (item, tile of the class's program): the tile's x cells and
+// block records arrive on one mbarrier; warp (row group, pole warp) walks its rows' records -- K*K broadcast
+// H values + K*C of its own x values from shared memory per K*K*C DFMAs -- and writes each finished row
+// straight to y: plain stores for rows the tile computes completely (beta = 0), RED.ADD.F64 for accumulating
+// sweeps and for the partial sums of the rows above a subtree tile (those rows are zeroed beforehand when beta = 0).
+// Two CTAs share an SM (<= 112 KB each): one computes while the other's tile is in flight.
+// ------------------------------------------------------------------------------------------
+constexpr int RT_MAXX = 40;        // x cells per tile
+constexpr int RT_MAXRG = 4;        // row groups (warps along the rows) per CTA
+
+struct RTTile {
+    int nx;                // x cells of the tile
+    int rec0, nrec;        // its block records (index into the program's record array)
+    int row0;              // first entry in the program's row array
+    int rg_end[RT_MAXRG];  // rows [rg_end[g-1], rg_end[g]) (relative to row0) belong to row group g
+    int xq[RT_MAXX];       // 1-D cell of x slot i
+};
+
+struct RTRow {
+    int q;                 // output 1-D cell
+    int rb, re;            // records [rb, re) relative to the tile's rec0
+    int partial;           // 1: a partial sum (always reduced into y)
+};
+
+struct RTWork {
+    int ctab;              // offset of the group's cell table
+    int lo, hi;            // item = lo + S * hi
+    int tile;
+};
+
+__global__ void zero_cells_kernel(double* __restrict__ Y, const int* __restrict__ cells, int ncells, int KDp) {
+    for (int c = blockIdx.x; c < ncells; c += gridDim.x) {
+        double2* dst = reinterpret_cast<double2*>(Y + (size_t)cells[c] * KDp);
+        for (int e = threadIdx.x; e < KDp / 2; e += blockDim.x) dst[e] = make_double2(0.0, 0.0);
+    }
+}
+
+template <int K, int C>
+__global__ void __launch_bounds__(256, 2)
+sweep_rowtile_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
+                     const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
+                     const RTWork* __restrict__ work, const RTTile* __restrict__ tiles, const RTRow* __restrict__ rows,
+                     const unsigned char* __restrict__ recs, int KDp, int A, int PI, int PW, int RG) {
+    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smraw);
+    double* xs = reinterpret_cast<double*>(smraw + 64);
+
+    const RTWork w = work[blockIdx.x];
+    const RTTile* __restrict__ T = tiles + w.tile;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    const int nx = T->nx, nrec = T->nrec;
+    const unsigned cell_bytes = (unsigned)KDp * 8u;
+    unsigned char* recs_s = smraw + 64 + (size_t)nx * cell_bytes;
+    const CellOfs* __restrict__ ctab = celltab + w.ctab;
+    const long long item_ofs = (long long)KDp * w.lo;
+
+    if (tid == 0) {
+        tma::mbar_init(tma::smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned b = tma::smem_u32(bar);
+        if (lane == 0) tma::mbar_expect_tx(b, (unsigned)nx * cell_bytes + (unsigned)nrec * REC);
+        __syncwarp();
+        for (int i = lane; i < nx; i += 32) {
+            const CellOfs co = ctab[T->xq[i]];
+            tma::bulk_g2s(tma::smem_u32(xs + (size_t)i * KDp), X + co.bq + item_ofs + co.kc * w.hi, cell_bytes, b);
+        }
+        if (lane == 0) tma::bulk_g2s(tma::smem_u32(recs_s), recs + (size_t)T->rec0 * REC, (unsigned)nrec * REC, b);
+    }
+    // per-lane pole constants: pole slot c of this lane = pole pw * 32 * C + c * 32 + lane
+    const int pw = warp % PW, rg = warp / PW;
+    int po[C];
+    bool ok[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = (pw * C + c) * 32 + lane;
+        ok[c] = j < PI;
+        po[c] = offtab[ok[c] ? j : 0];
+    }
+    const int r_begin = T->row0 + (rg == 0 ? 0 : T->rg_end[rg - 1]), r_end = T->row0 + T->rg_end[rg];
+    const unsigned xs_s = tma::smem_u32(xs), rs_s = tma::smem_u32(recs_s);
+    tma::mbar_wait(tma::smem_u32(bar), 0);
+
+    if (rg < RG)
+    for (int ri = r_begin; ri < r_end; ++ri) {
+        const RTRow row = rows[ri];
+        double acc[K][C];
+#pragma unroll
+        for (int m = 0; m < K; ++m)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[m][c] = 0.0;
+#pragma unroll 2
+        for (int rec = row.rb; rec < row.re; ++rec) {
+            const unsigned ra = rs_s + rec * REC;
+            double h[KK];
+            unsigned xa;
+            if constexpr ((KK & 1) == 1) {          // odd K*K: the last 16-byte load carries h[KK-1] and the x offset
+#pragma unroll
+                for (int e = 0; e + 1 < KK; e += 2) lds_v2f64(h[e], h[e + 1], ra + e * 8);
+                double metad;
+                lds_v2f64(h[KK - 1], metad, ra + (KK - 1) * 8);
+                xa = xs_s + (unsigned)__double2loint(metad);
+            } else {
+#pragma unroll
+                for (int e = 0; e < KK; e += 2) lds_v2f64(h[e], h[e + 1], ra + e * 8);
+                xa = xs_s + (unsigned)lds_v2s32(ra + KK * 8).x;
+            }
+            double xv[K][C];
+#pragma unroll
+            for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                for (int c = 0; c < C; ++c) xv[mi][c] = lds_f64(xa + (po[c] + A * mi) * 8);
+#pragma unroll
+            for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[mo][c] = fma(h[mo * K + mi], xv[mi][c], acc[mo][c]);
+        }
+        const CellOfs co = ctab[row.q];
+        double* yrow = Y + co.bq + item_ofs + co.kc * w.hi;
+        const bool red = accumulate != 0 || row.partial != 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int mo = 0; mo < K; ++mo)
+                if (ok[c]) {
+                    if (red) atomicAdd(yrow + po[c] + A * mo, alpha * acc[mo][c]);      // RED.ADD.F64
+                    else yrow[po[c] + A * mo] = alpha * acc[mo][c];
+                }
+    }
+}
+
 // development aid: a spinner with a chosen resource footprint, to probe which kernels share an SM
 __global__ void debug_spin_kernel(long long* __restrict__ dbg, int slot, int ns) {
     extern __shared__ __align__(128) unsigned char smraw[];

@@ -102,6 +102,15 @@ int gsg_plan_sync(gsg_plan* plan);
  * no partition); 2 (default): automatic -- flat for small index sets (N * D <= 6e6: BASELINE configs 2 and 3,
  * where a step is launch-latency bound), tiled above.  The environment variable GSG_FLAT sets the initial mode. */
 int gsg_plan_set_flat(gsg_plan* plan, int mode);
+/* CPU-side check of the row-tile kernel's tile program (no device needed) for pole class p of the library's own
+ * H = periodic_DLF_matrix(k, n) and multi-cells of k^D doubles; budget_bytes = shared memory per tile, nrg = row
+ * groups.  Two-call pattern: NULL outputs return counts_out = {tiles, rows, records}.  tiles_out: 48 int32 per tile
+ * {nx, rec0, nrec, row0, rg_end[4], xq[40]}; rows_out: 4 int32 per row {q, rb, re, partial}; rec_h_out: k*k doubles
+ * per record; rec_slot_out: the x slot of each record. */
+int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out,
+                              int32_t* rows_out, double* rec_h_out, int32_t* rec_slot_out, int64_t* counts_out);
+/* human-readable summary: which kernel serves which pole classes in every direction ("kind(p, tiles)") */
+int gsg_plan_describe(const gsg_plan* plan, char* buf, size_t buflen);
 /* 1 if the operator applies of this plan currently take the flat kernel */
 int gsg_plan_flat_active(const gsg_plan* plan, int* active_out);
 /* CPU-side check of the flat path's tables (no device needed): pole groups of direction d (1-based) and, for

@@ -86,18 +86,25 @@ def flat_tables(D: int, k: int, n: int, d: int, scheme: str = "sparse"):
     return groups, cells
 
 
-def rowtile_program(D: int, k: int, n: int, p: int, budget_bytes: int = 112 * 1024, nrg: int = 2):
+def rowtile_program(D: int, k: int, n: int, p: int, budget_bytes: int = 226 * 1024, nrg: int = 4):
     """CPU-side copy of the row-tile kernel's tile program for pole class p (library's own H(k, n), multi-cells of
-    k^D doubles): dict with tiles [nt, 48] int32, rows [nr, 4] int32, rec_h [nrec, k, k], rec_slot [nrec]."""
+    k^D doubles): dict with tiles [nt, 48] int32 {nx, rec_ofs, rec_bytes, grp0, rg_end[4], xq[40]}, groups [ng, 8]
+    int32 {q[4], rofs, nrec, partial mask, 0} and the record blob (bytes)."""
     cnt = (C.c_int64 * 3)()
-    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, None, None, None, None, cnt))
+    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, None, None, None, cnt))
     tiles = np.zeros((cnt[0], 48), dtype=np.int32)
-    rows = np.zeros((cnt[1], 4), dtype=np.int32)
-    rec_h = np.zeros((cnt[2], k, k))
-    rec_slot = np.zeros(cnt[2], dtype=np.int32)
+    groups = np.zeros((cnt[1], 8), dtype=np.int32)
+    blob = np.zeros(cnt[2], dtype=np.uint8)
     vp_ = lambda a: a.ctypes.data_as(C.c_void_p)
-    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, vp_(tiles), vp_(rows), vp_(rec_h), vp_(rec_slot), cnt))
-    return {"tiles": tiles, "rows": rows, "rec_h": rec_h, "rec_slot": rec_slot}
+    check(lib.gsg_debug_rowtile_program(D, k, n, p, budget_bytes, nrg, vp_(tiles), vp_(groups), vp_(blob), cnt))
+    return {"tiles": tiles, "groups": groups, "blob": blob}
+
+
+def rowtile_pole_order(k: int, A: int, PI: int, nslots: int) -> np.ndarray:
+    """lane order of the row-tile kernel: in-cell pole offsets, padding lanes as ~offset"""
+    out = np.zeros(nslots, dtype=np.int32)
+    check(lib.gsg_debug_rowtile_pole_order(k, A, PI, nslots, out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def get_size(D: int, k: int, n: int, scheme: str = "sparse") -> int:

@@ -76,7 +76,8 @@ SIGNATURES = {
     "gsg_plan_set_flat": (i32, [vp, i32]),
     "gsg_plan_flat_active": (i32, [vp, C.POINTER(i32)]),
     "gsg_plan_describe": (i32, [vp, C.c_char_p, C.c_size_t]),
-    "gsg_debug_rowtile_program": (i32, [i32, i32, i32, i32, i64, i32, vp, vp, vp, vp, p_i64]),
+    "gsg_debug_rowtile_program": (i32, [i32, i32, i32, i32, i64, i32, vp, vp, vp, p_i64]),
+    "gsg_debug_rowtile_pole_order": (i32, [i32, i32, i32, i32, vp]),
     "gsg_debug_flat_tables": (i32, [i32, i32, i32, i32, i32, vp, vp, p_i64, p_i64]),
     "gsg_ode_create": (i32, [vp, i32, vp, vp, i32, f64, f64, vp, f64, f64, C.POINTER(vp)]),
     "gsg_ode_destroy": (i32, [vp]),

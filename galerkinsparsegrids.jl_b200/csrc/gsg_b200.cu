@@ -8,6 +8,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -124,6 +125,7 @@ struct SweepClass {          // one launch of a sweep
     DevBuf<TileS> stiles;
     DevBuf<TileS2> s2tiles;     // second-generation streaming kernel
     DevBuf<RTWork> rtwork;      // row-tile kernel: (item, tile) work list, heaviest tiles first
+    DevBuf<long long> rtsrc;    // ... and per work item the offsets in x of the tile's RT_MAXX cells
     DevBuf<int> rtzero;         // ... and the multi-cells that receive partial sums (zeroed before a beta = 0 sweep)
     bool stream2 = false;
     ShortParams sprm{};
@@ -215,7 +217,7 @@ struct gsg_plan {
     size_t rt_smem = 0;
     RTProgram rt_prog;
     DevBuf<RTTile> rt_tiles;
-    DevBuf<RTRow> rt_rows;
+    DevBuf<RTGroup> rt_groups;
     DevBuf<unsigned char> rt_recs;
 
     // flat path (kernels.cuh, sweep_flat_kernel): one launch per right-hand side for small index sets.
@@ -297,39 +299,42 @@ void block_csr_from_dense(const std::vector<double>& Hd, const std::vector<char>
 // Row-tile kernel for the long-pole classes: eligible when an item has enough poles to fill the lanes (k^(D-1) >= 64,
 // i.e. the big index sets: D = 6 / 5 at k = 3, D = 4 at k = 4, 5) and the program fits.  GSG_ROWTILE=0 turns it off
 // (the constant-bank / register-tiled kernels then serve those classes), GSG_RT_BUDGET_KB sets the shared-memory
-// budget of a tile (default 112 KB: two CTAs per SM).
+// budget of a tile (default 225 KB: one CTA per SM, the fewest partial sums), GSG_RT_C the poles per lane.
 int build_rowtile_program(gsg_plan& P) {
     P.rt_on = false;
     const int K = P.S.k, n = P.S.n;
     const int PI = (int)(P.S.kD / K);
     const char* env = getenv("GSG_ROWTILE");
-    if (!env || atoi(env) == 0) return 0;                 // opt-in while it is being measured
+    if (env && atoi(env) == 0) return 0;
     if (K > 5 || PI < 64 || PI > 512) return 0;
     int pmin = 0;
     while (pmin <= n && short_supported(K, pmin)) ++pmin;
     if (pmin > n) return 0;
-    size_t budget = 112 * 1024;
+    size_t budget = SMEM_OPTIN_MAX - 1024;                // measured at D=6, k=3, n=8: one big tile per SM beats two of half the size
     if (const char* e = getenv("GSG_RT_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
     budget = std::min(budget, SMEM_OPTIN_MAX - 1024);
-    P.rt_C = PI > 96 ? 2 : 1;
+    P.rt_C = (PI >= 192 && K <= 3) ? 4 : PI > 96 ? 2 : 1;
     if (const char* e = getenv("GSG_RT_C")) {
         const int c = atoi(e);
         if (c == 1 || c == 2 || (c == 4 && K <= 3)) P.rt_C = c;
     }
     P.rt_PW = (PI + 32 * P.rt_C - 1) / (32 * P.rt_C);
     if (P.rt_PW > 8) return 0;
-    P.rt_RG = std::max(1, std::min(RT_MAXRG, 8 / P.rt_PW));
+    int nwarps = 8;
+    if (const char* e = getenv("GSG_RT_WARPS"))
+        if (atoi(e) == 16 && K <= 3 && P.rt_C <= 2) nwarps = 16;
+    P.rt_RG = std::max(1, std::min(RT_MAXRG, nwarps / P.rt_PW));
     if (rt_build_program(P.h_rowptr, P.h_col, P.h_val, P.KK2, K, (int)P.S.kDp, n, pmin, budget, P.rt_RG, P.rt_prog) != 0) {
         P.rt_prog = RTProgram();
         return 0;                                         // no tiling fits: the other kernels serve these classes
     }
     size_t need = 0;
     for (const RTTile& T : P.rt_prog.tiles)
-        need = std::max(need, (size_t)64 + (size_t)T.nx * P.S.kDp * 8 + (size_t)T.nrec * P.rt_prog.rec_bytes);
+        need = std::max(need, (size_t)64 + (size_t)(2 * P.rt_RG + T.nx) * P.S.kDp * 8 + (size_t)T.rec_bytes);
     P.rt_smem = need;
     GSG_TRY(P.rt_tiles.upload(P.rt_prog.tiles));
-    GSG_TRY(P.rt_rows.upload(P.rt_prog.rows));
-    GSG_TRY(P.rt_recs.upload(P.rt_prog.recs));
+    GSG_TRY(P.rt_groups.upload(P.rt_prog.groups));
+    GSG_TRY(P.rt_recs.upload(P.rt_prog.blob));
     P.rt_pmin = pmin;
     P.rt_on = true;
     return 0;
@@ -682,15 +687,7 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
     // ---- row-tile class: every long-pole class p >= rt_pmin in ONE launch, CTA = (item, tile of the class's program)
     const bool rowtile = P.rt_on && tma_active;
     if (rowtile) {
-        std::vector<int> ot(PI);
-        const int B = PI / dir.A;
-        static const bool plain = getenv("GSG_RT_PLAIN_ORDER") != nullptr;
-        for (int j = 0; j < PI; ++j) {
-            int a, b;
-            if (dir.A >= 16 || B == 1 || plain) { a = j % dir.A; b = j / dir.A; }
-            else { b = j % B; a = j / B; }
-            ot[j] = a + K * dir.A * b;
-        }
+        const std::vector<int> ot = rt_pole_order(K, dir.A, PI, 32 * P.rt_C * P.rt_PW);
         GSG_TRY(dir.rt_offtab.upload(ot));
         SweepClass c;
         c.kind = Kind::ROWTILE;
@@ -711,7 +708,11 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
             }
             for (int r = 0; r < g.nitems; ++r) {
                 const int lo = r % g.S, hi = r / g.S;
-                for (int t = 0; t < P.rt_prog.cls_count[g.p]; ++t) work.push_back(RTWork{ctab, lo, hi, P.rt_prog.cls_first[g.p] + t});
+                for (int t = 0; t < P.rt_prog.cls_count[g.p]; ++t) {
+                    const int ti = P.rt_prog.cls_first[g.p] + t;
+                    const RTTile& T = P.rt_prog.tiles[ti];
+                    work.push_back(RTWork{ctab, lo, hi, ti, T.nx, T.rec_ofs, T.rec_bytes, 0});
+                }
                 for (int q : P.rt_prog.cls_partial_q[g.p]) {
                     const CellOfs& co = celltab[ctab + q];
                     zero.push_back((int)((co.bq + (long long)KDp * lo + co.kc * hi) / KDp));
@@ -720,10 +721,20 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
         }
         if (!work.empty()) {
             std::stable_sort(work.begin(), work.end(), [&](const RTWork& a, const RTWork& b) {
-                return P.rt_prog.tiles[a.tile].nrec > P.rt_prog.tiles[b.tile].nrec;
+                return P.rt_prog.tiles[a.tile].rec_bytes > P.rt_prog.tiles[b.tile].rec_bytes;
             });
             c.ntiles = (int)work.size();
             c.smem = P.rt_smem;
+            std::vector<long long> src(work.size() * (size_t)RT_MAXX, 0);
+            for (size_t wi = 0; wi < work.size(); ++wi) {
+                const RTWork& w = work[wi];
+                const RTTile& T = P.rt_prog.tiles[w.tile];
+                for (int i = 0; i < T.nx; ++i) {
+                    const CellOfs& co = celltab[w.ctab + T.xq[i]];
+                    src[wi * RT_MAXX + i] = co.bq + (long long)KDp * w.lo + co.kc * w.hi;
+                }
+            }
+            GSG_TRY(c.rtsrc.upload(src));
             GSG_TRY(c.rtwork.upload(work));
             GSG_TRY(c.rtzero.upload(zero));
             dir.classes.push_back(std::move(c));
@@ -1313,7 +1324,7 @@ int launch_rowtile_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
                      double* y, double alpha, double beta) {
     if constexpr (K >= 1 && K <= 5) {
         if (c.ntiles == 0) return 0;
-        const int PI = (int)pl.S.kD / K, KDp = (int)pl.S.kDp;
+        const int KDp = (int)pl.S.kDp;
         if (beta == 0.0 && c.rtzero.n > 0) {      // rows that only receive partial sums start from zero
             const int nz = (int)c.rtzero.n;
             zero_cells_kernel<<<std::min(nz, pl.sm_count * 8), 128, 0, st>>>(y, c.rtzero.p, nz, KDp);
@@ -1324,12 +1335,20 @@ int launch_rowtile_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
             static thread_local size_t configured = 0;
             GSG_TRY(ensure_smem(kern, c.smem, configured));
             kern<<<c.ntiles, threads, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.rt_offtab.p, c.rtwork.p,
-                                                     pl.rt_tiles.p, pl.rt_rows.p, pl.rt_recs.p, KDp, dir.A, PI, pl.rt_PW, pl.rt_RG);
+                                                     c.rtsrc.p, pl.rt_tiles.p, pl.rt_groups.p, pl.rt_recs.p, KDp, dir.A, pl.rt_PW,
+                                                     pl.rt_RG, pl.dbg);
             return 0;
         };
-        if (pl.rt_C == 4) { if constexpr (K <= 3) GSG_TRY(go(sweep_rowtile_kernel<K, 4>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 4 for k > 3"); }
-        else if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2>));
-        else GSG_TRY(go(sweep_rowtile_kernel<K, 1>));
+        if (threads > 256) {                      // 16 warps (GSG_RT_WARPS=16): 128 registers per thread, C <= 2 at k <= 3
+            if constexpr (K <= 3) {
+                if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2, 512>));
+                else if (pl.rt_C == 1) GSG_TRY(go(sweep_rowtile_kernel<K, 1, 512>));
+                else return fail(GSG_ERR_UNSUPPORTED, "internal: 16-warp row-tile kernel needs C <= 2");
+            } else return fail(GSG_ERR_UNSUPPORTED, "internal: 16-warp row-tile kernel needs k <= 3");
+        }
+        else if (pl.rt_C == 4) { if constexpr (K <= 3) GSG_TRY(go(sweep_rowtile_kernel<K, 4, 256>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 4 for k > 3"); }
+        else if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2, 256>));
+        else GSG_TRY(go(sweep_rowtile_kernel<K, 1, 256>));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_rowtile", K, c);
     }
@@ -2232,10 +2251,11 @@ int gsg_debug_flat_tables(int D, int k, int n, int scheme, int d, int64_t* group
 
 // CPU-side check of the row-tile program (no device needed): the tile program of pole class p for the library's own
 // H = periodic_DLF_matrix(k, n), multi-cells of k^D doubles.  Two-call pattern: NULL outputs return the counts
-// {tiles, rows, records}.  tiles_out: (8 + 40) int32 per tile {nx, rec0, nrec, row0, rg_end[4], xq[40]}; rows_out:
-// 4 int32 per row {q, rb, re, partial}; rec_h_out: k*k doubles per record (row-major); rec_slot_out: x slot per record.
-int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out, int32_t* rows_out,
-                              double* rec_h_out, int32_t* rec_slot_out, int64_t* counts_out) {
+// {tiles, groups, blob bytes}.  tiles_out: (8 + 40) int32 per tile {nx, rec_ofs, rec_bytes, grp0, rg_end[4], xq[40]};
+// groups_out: 8 int32 per group {q[4], rofs, nrec, partial, 0}; blob_out: the record bytes ({int32 x cell byte offset,
+// int32 row mask} + one k x k block of doubles, row-major, per mask bit).
+int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out, int32_t* groups_out,
+                              unsigned char* blob_out, int64_t* counts_out) {
     GSG_TRY(check_dkn(D, k, n, 0));
     if (p < 0 || p > n || !counts_out) return fail(GSG_ERR_ARG, "bad argument");
     const gsg::Csc H = gsg::periodic_hier_DLF_matrix(k, n);
@@ -2258,31 +2278,28 @@ int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, 
     const int KDp = (int)((kD + 1) & ~int64_t(1));
     RTProgram prog;
     GSG_TRY(rt_build_program(rowptr, col, val, KK2, k, KDp, p, p, (size_t)budget_bytes, nrg, prog));
-    const int64_t nrec = (int64_t)(prog.recs.size() / prog.rec_bytes);
     counts_out[0] = (int64_t)prog.tiles.size();
-    counts_out[1] = (int64_t)prog.rows.size();
-    counts_out[2] = nrec;
+    counts_out[1] = (int64_t)prog.groups.size();
+    counts_out[2] = (int64_t)prog.blob.size();
     if (tiles_out)
         for (size_t t = 0; t < prog.tiles.size(); ++t) {
             const RTTile& T = prog.tiles[t];
             int32_t* o = tiles_out + t * (8 + RT_MAXX);
-            o[0] = T.nx; o[1] = T.rec0; o[2] = T.nrec; o[3] = T.row0;
+            o[0] = T.nx; o[1] = T.rec_ofs; o[2] = T.rec_bytes; o[3] = T.grp0;
             for (int g = 0; g < RT_MAXRG; ++g) o[4 + g] = T.rg_end[g];
             for (int i = 0; i < RT_MAXX; ++i) o[8 + i] = T.xq[i];
         }
-    if (rows_out)
-        for (size_t r = 0; r < prog.rows.size(); ++r) {
-            rows_out[4 * r] = prog.rows[r].q; rows_out[4 * r + 1] = prog.rows[r].rb;
-            rows_out[4 * r + 2] = prog.rows[r].re; rows_out[4 * r + 3] = prog.rows[r].partial;
-        }
-    if (rec_h_out && rec_slot_out)
-        for (int64_t r = 0; r < nrec; ++r) {
-            const unsigned char* rec = prog.recs.data() + (size_t)r * prog.rec_bytes;
-            std::memcpy(rec_h_out + r * k * k, rec, (size_t)k * k * 8);
-            int meta[2];
-            std::memcpy(meta, rec + (size_t)k * k * 8, 8);
-            rec_slot_out[r] = meta[0] / (KDp * 8);
-        }
+    if (groups_out) std::memcpy(groups_out, prog.groups.data(), prog.groups.size() * sizeof(RTGroup));
+    if (blob_out) std::memcpy(blob_out, prog.blob.data(), prog.blob.size());
+    return 0;
+}
+
+// CPU-side check of the row-tile kernel's lane order: the nslots = 32 * C * PW table entries for in-cell stride A
+// (padding lanes as ~offset)
+int gsg_debug_rowtile_pole_order(int k, int A, int PI, int nslots, int32_t* out) {
+    if (k < 1 || A < 1 || PI < 1 || PI % A != 0 || nslots < PI || nslots % 32 != 0 || !out) return fail(GSG_ERR_ARG, "bad argument");
+    const std::vector<int> t = rt_pole_order(k, A, PI, nslots);
+    std::memcpy(out, t.data(), t.size() * sizeof(int));
     return 0;
 }
 

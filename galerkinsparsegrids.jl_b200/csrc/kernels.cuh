@@ -1273,36 +1273,46 @@ sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double
 // ------------------------------------------------------------------------------------------
 // Long poles, ROW-TILE kernel (N' >= 48 when an item has >= 64 poles; rowtile.inl builds the tile programs).
 // Unit of data movement = the whole multi-cell (all k^(D-1) poles of an item for one 1-D cell: ONE contiguous,
-// 16-byte aligned run), so the x tile is staged with a handful of TMA bulk copies (UBLKCP) instead of 8-byte
-// gathers, lanes = poles (C per lane), and a CTA = (item, tile of the class's program): the tile's x cells and
-// block records arrive on one mbarrier; warp (row group, pole warp) walks its rows' records -- K*K broadcast
-// H values + K*C of its own x values from shared memory per K*K*C DFMAs -- and writes each finished row
-// straight to y: plain stores for rows the tile computes completely (beta = 0), RED.ADD.F64 for accumulating
-// sweeps and for the partial sums of the rows above a subtree tile (those rows are zeroed beforehand when beta = 0).
-// Two CTAs share an SM (<= 112 KB each): one computes while the other's tile is in flight.
+// 16-byte aligned run): the x tile is staged with a handful of TMA bulk copies (UBLKCP), lanes = poles (C per
+// lane, in a bank-permuted order: the 16 lanes of a half-warp read 16 different 8-byte banks), and a
+// CTA = (item, tile of the class's program): the tile's x cells and block records arrive on one mbarrier.
+// Warp (row group, pole warp) walks its ROW GROUPS: up to RT_R output rows that share most of their columns are
+// accumulated together, so an x value read from shared memory feeds up to RT_R * K DFMAs and a broadcast H value
+// feeds C: the loop is bound by the fp64 pipe, not by shared-memory wavefronts.  A record = {x cell, row mask}
+// followed by one K x K block per row of the mask (uniform branches).  Finished rows go through a per-row-group
+// staging cell in shared memory and leave as ONE bulk store (complete rows, beta = 0) or bulk reduce-add
+// (UBLKRED.ADD.F64: accumulating sweeps and the partial sums of rows above a subtree tile -- those rows are zeroed
+// beforehand when beta = 0), so y is written in whole 16-byte aligned multi-cells whatever the lane order.
 // ------------------------------------------------------------------------------------------
 constexpr int RT_MAXX = 40;        // x cells per tile
 constexpr int RT_MAXRG = 4;        // row groups (warps along the rows) per CTA
+constexpr int RT_R = 4;            // output rows accumulated together
 
 struct RTTile {
     int nx;                // x cells of the tile
-    int rec0, nrec;        // its block records (index into the program's record array)
-    int row0;              // first entry in the program's row array
-    int rg_end[RT_MAXRG];  // rows [rg_end[g-1], rg_end[g]) (relative to row0) belong to row group g
+    int rec_ofs;           // byte offset of its record blob in the program's blob (multiple of 16)
+    int rec_bytes;         // bytes of the blob (multiple of 16)
+    int grp0;              // first entry in the program's group array
+    int rg_end[RT_MAXRG];  // groups [rg_end[g-1], rg_end[g]) (relative to grp0) belong to row group g
     int xq[RT_MAXX];       // 1-D cell of x slot i
 };
 
-struct RTRow {
-    int q;                 // output 1-D cell
-    int rb, re;            // records [rb, re) relative to the tile's rec0
-    int partial;           // 1: a partial sum (always reduced into y)
+struct RTGroup {
+    int q[RT_R];           // output 1-D cells (-1: unused)
+    int rofs;              // byte offset of the group's first record inside the tile's blob
+    int nrec;              // records (= distinct x cells of the group)
+    int partial;           // bit r: row r is a partial sum (always reduced into y)
+    int pad;
 };
 
 struct RTWork {
     int ctab;              // offset of the group's cell table
     int lo, hi;            // item = lo + S * hi
     int tile;
+    int nx, rec_ofs, rec_bytes, pad;   // copies of the tile's fields (one dependent load less before the first bulk copy)
 };
+
+constexpr int RT_NBAR = 4;         // the x cells of a tile arrive on RT_NBAR barriers (records with the first)
 
 __global__ void zero_cells_kernel(double* __restrict__ Y, const int* __restrict__ cells, int ncells, int KDp) {
     for (int c = blockIdx.x; c < ncells; c += gridDim.x) {
@@ -1311,104 +1321,178 @@ __global__ void zero_cells_kernel(double* __restrict__ Y, const int* __restrict_
     }
 }
 
-template <int K, int C>
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// shared memory: [RT_NBAR barriers (64 B)] [2 * RG staging cells] [nx x cells] [records]
+template <int K, int C, int NT>
+__global__ void __launch_bounds__(NT, 1)
 sweep_rowtile_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                      const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
-                     const RTWork* __restrict__ work, const RTTile* __restrict__ tiles, const RTRow* __restrict__ rows,
-                     const unsigned char* __restrict__ recs, int KDp, int A, int PI, int PW, int RG) {
-    constexpr int KK = K * K, REC = LongRec<K>::BYTES;
+                     const RTWork* __restrict__ work, const long long* __restrict__ xsrc,
+                     const RTTile* __restrict__ tiles, const RTGroup* __restrict__ groups,
+                     const unsigned char* __restrict__ recs, int KDp, int A, int PW, int RG,
+                     long long* __restrict__ dbg) {      // dbg: optional per-CTA time stamps (tools/stamps_rowtile.py)
+    constexpr int KK = K * K;
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smraw);
-    double* xs = reinterpret_cast<double*>(smraw + 64);
+    const unsigned cell_bytes = (unsigned)KDp * 8u;
+    const long long g_t0 = dbg ? gtimer() : 0;
+    long long t_main = 0, t_epi = 0;
+    double* stage = reinterpret_cast<double*>(smraw + 64);                       // 2 * RG staging cells
+    double* xs = reinterpret_cast<double*>(smraw + 64 + (size_t)2 * RG * cell_bytes);
 
-    const RTWork w = work[blockIdx.x];
-    const RTTile* __restrict__ T = tiles + w.tile;
     const int tid = threadIdx.x, warp = tid >> 5;
     int lane = tid & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));
-    const int nx = T->nx, nrec = T->nrec;
-    const unsigned cell_bytes = (unsigned)KDp * 8u;
-    unsigned char* recs_s = smraw + 64 + (size_t)nx * cell_bytes;
-    const CellOfs* __restrict__ ctab = celltab + w.ctab;
-    const long long item_ofs = (long long)KDp * w.lo;
+    // the only loads in front of the bulk copies: the work item and (independent of it) the source offsets of its cells
+    const int4 w0 = *reinterpret_cast<const int4*>(work + blockIdx.x);           // ctab, lo, hi, tile
+    const int4 w1 = *(reinterpret_cast<const int4*>(work + blockIdx.x) + 1);     // nx, rec_ofs, rec_bytes
+    const int nx = w1.x;
+    const unsigned rec_bytes = (unsigned)w1.z;
+    unsigned char* recs_s = reinterpret_cast<unsigned char*>(xs) + (size_t)nx * cell_bytes;
 
     if (tid == 0) {
-        tma::mbar_init(tma::smem_u32(bar), 1);
+#pragma unroll
+        for (int b = 0; b < RT_NBAR; ++b) tma::mbar_init(tma::smem_u32(bar + b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 2 * RG) stage[(size_t)tid * KDp + KDp - 1] = 0.0;        // the padding slot of a multi-cell stays zero
     __syncthreads();
     if (warp == 0) {
-        const unsigned b = tma::smem_u32(bar);
-        if (lane == 0) tma::mbar_expect_tx(b, (unsigned)nx * cell_bytes + (unsigned)nrec * REC);
-        __syncwarp();
-        for (int i = lane; i < nx; i += 32) {
-            const CellOfs co = ctab[T->xq[i]];
-            tma::bulk_g2s(tma::smem_u32(xs + (size_t)i * KDp), X + co.bq + item_ofs + co.kc * w.hi, cell_bytes, b);
+        // cell i arrives on barrier (i * RT_NBAR) / nx, the records on barrier 0
+        if (lane < RT_NBAR) {
+            const int c0 = (lane * nx + RT_NBAR - 1) / RT_NBAR, c1 = ((lane + 1) * nx + RT_NBAR - 1) / RT_NBAR;
+            tma::mbar_expect_tx(tma::smem_u32(bar + lane), (unsigned)(c1 - c0) * cell_bytes + (lane == 0 ? rec_bytes : 0u));
         }
-        if (lane == 0) tma::bulk_g2s(tma::smem_u32(recs_s), recs + (size_t)T->rec0 * REC, (unsigned)nrec * REC, b);
+        __syncwarp();
+        if (lane == 0) tma::bulk_g2s(tma::smem_u32(recs_s), recs + w1.y, rec_bytes, tma::smem_u32(bar));
+        for (int i = lane; i < nx; i += 32)
+            tma::bulk_g2s(tma::smem_u32(xs + (size_t)i * KDp), X + xsrc[(size_t)blockIdx.x * RT_MAXX + i], cell_bytes,
+                          tma::smem_u32(bar + (i * RT_NBAR) / nx));
     }
-    // per-lane pole constants: pole slot c of this lane = pole pw * 32 * C + c * 32 + lane
+    const RTTile* __restrict__ T = tiles + w0.w;
+    const CellOfs* __restrict__ ctab = celltab + w0.x;
+    const long long item_ofs = (long long)KDp * w0.y;
+    // per-lane pole constants: pole slot c of this lane = entry (pw * C + c) * 32 + lane of the bank-permuted table;
+    // a negative entry ~o marks a padding lane (it reads pole offset o like a neighbour and stores nothing)
     const int pw = warp % PW, rg = warp / PW;
-    int po[C];
+    unsigned pob[C];
     bool ok[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const int j = (pw * C + c) * 32 + lane;
-        ok[c] = j < PI;
-        po[c] = offtab[ok[c] ? j : 0];
+        const int v = offtab[(pw * C + c) * 32 + lane];
+        ok[c] = v >= 0;
+        pob[c] = (unsigned)(v >= 0 ? v : ~v) * 8u;
     }
-    const int r_begin = T->row0 + (rg == 0 ? 0 : T->rg_end[rg - 1]), r_end = T->row0 + T->rg_end[rg];
+    const unsigned A8 = (unsigned)A * 8u;
+    const int g_begin = T->grp0 + (rg == 0 ? 0 : T->rg_end[rg - 1]), g_end = T->grp0 + T->rg_end[rg];
     const unsigned xs_s = tma::smem_u32(xs), rs_s = tma::smem_u32(recs_s);
+    const unsigned st_s = tma::smem_u32(stage) + (unsigned)(2 * rg) * cell_bytes;
+    const bool issuer = pw == 0 && lane == 0;
+    const int nbar = 32 * PW;
+    if (g_begin >= g_end) return;
+    int4 gq = *reinterpret_cast<const int4*>(groups + g_begin);
+    int4 gm = *(reinterpret_cast<const int4*>(groups + g_begin) + 1);             // rofs, nrec, partial, pad
     tma::mbar_wait(tma::smem_u32(bar), 0);
+    const long long g_t1 = dbg ? gtimer() : 0;
+    unsigned arrived = 1u;                  // barriers this warp has seen complete
+    unsigned sbuf = 0;                      // staging cell of the next row (alternates)
 
-    if (rg < RG)
-    for (int ri = r_begin; ri < r_end; ++ri) {
-        const RTRow row = rows[ri];
-        double acc[K][C];
+    for (int gi = g_begin; gi < g_end; ++gi) {
+        const int4 cq = gq, cm = gm;
+        if (gi + 1 < g_end) {               // next group's descriptor while this one is computed
+            gq = *reinterpret_cast<const int4*>(groups + gi + 1);
+            gm = *(reinterpret_cast<const int4*>(groups + gi + 1) + 1);
+        }
+        const int qs[RT_R] = {cq.x, cq.y, cq.z, cq.w};
+        long long yofs[RT_R];               // output cells, fetched now and used in the epilogue
 #pragma unroll
-        for (int m = 0; m < K; ++m)
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[m][c] = 0.0;
-#pragma unroll 2
-        for (int rec = row.rb; rec < row.re; ++rec) {
-            const unsigned ra = rs_s + rec * REC;
-            double h[KK];
-            unsigned xa;
-            if constexpr ((KK & 1) == 1) {          // odd K*K: the last 16-byte load carries h[KK-1] and the x offset
-#pragma unroll
-                for (int e = 0; e + 1 < KK; e += 2) lds_v2f64(h[e], h[e + 1], ra + e * 8);
-                double metad;
-                lds_v2f64(h[KK - 1], metad, ra + (KK - 1) * 8);
-                xa = xs_s + (unsigned)__double2loint(metad);
-            } else {
-#pragma unroll
-                for (int e = 0; e < KK; e += 2) lds_v2f64(h[e], h[e + 1], ra + e * 8);
-                xa = xs_s + (unsigned)lds_v2s32(ra + KK * 8).x;
+        for (int r = 0; r < RT_R; ++r) {
+            yofs[r] = 0;
+            if (issuer && qs[r] >= 0) {
+                const CellOfs co = ctab[qs[r]];
+                yofs[r] = co.bq + item_ofs + co.kc * w0.z;
             }
+        }
+        double acc[RT_R][K][C];
+#pragma unroll
+        for (int r = 0; r < RT_R; ++r)
+#pragma unroll
+            for (int m = 0; m < K; ++m)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[r][m][c] = 0.0;
+        unsigned ptr = rs_s + (unsigned)cm.x;
+        const long long c_0 = dbg ? clock64() : 0;
+        for (int i = 0; i < cm.y; ++i) {
+            const int2 hd = lds_v2s32(ptr);          // x cell offset (bytes); row mask | barrier of the cell << 8
+            ptr += 8;
+            const unsigned bi = ((unsigned)hd.y >> 8) & (RT_NBAR - 1);
+            if (!((arrived >> bi) & 1u)) {           // uniform over the warp
+                tma::mbar_wait(tma::smem_u32(bar + bi), 0);
+                arrived |= 1u << bi;
+            }
+            const unsigned xa = xs_s + (unsigned)hd.x;
             double xv[K][C];
 #pragma unroll
             for (int mi = 0; mi < K; ++mi)
 #pragma unroll
-                for (int c = 0; c < C; ++c) xv[mi][c] = lds_f64(xa + (po[c] + A * mi) * 8);
+                for (int c = 0; c < C; ++c) xv[mi][c] = lds_f64(xa + pob[c] + A8 * mi);
 #pragma unroll
-            for (int mi = 0; mi < K; ++mi)
+            for (int r = 0; r < RT_R; ++r) {
+                if (hd.y & (1 << r)) {               // uniform over the CTA's lanes
+                    double h[KK];
+#pragma unroll
+                    for (int e = 0; e < KK; ++e) h[e] = lds_f64(ptr + e * 8);
+                    ptr += KK * 8;
+#pragma unroll
+                    for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                        for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                            for (int c = 0; c < C; ++c) acc[r][mo][c] = fma(h[mo * K + mi], xv[mi][c], acc[r][mo][c]);
+                }
+            }
+        }
+        const long long c_1 = dbg ? clock64() : 0;
+#pragma unroll
+        for (int r = 0; r < RT_R; ++r) {
+            if (qs[r] < 0) continue;
+            const unsigned sb = st_s + sbuf * cell_bytes;
+            if (issuer) bulk_wait_read1();               // the bulk operation issued from this staging cell two rows ago has read it
+            named_bar_sync(1 + rg, nbar);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
 #pragma unroll
                 for (int mo = 0; mo < K; ++mo)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) acc[mo][c] = fma(h[mo * K + mi], xv[mi][c], acc[mo][c]);
+                    if (ok[c]) sts_f64(sb + pob[c] + A8 * mo, alpha * acc[r][mo][c]);
+            tma::fence_proxy_async();
+            named_bar_sync(1 + rg, nbar);
+            if (issuer) {
+                double* yrow = Y + yofs[r];
+                if (accumulate != 0 || ((cm.z >> r) & 1)) tma::bulk_red_add_f64(yrow, sb, cell_bytes);
+                else tma::bulk_s2g(yrow, sb, cell_bytes);
+                tma::bulk_commit();
+            }
+            sbuf ^= 1u;
         }
-        const CellOfs co = ctab[row.q];
-        double* yrow = Y + co.bq + item_ofs + co.kc * w.hi;
-        const bool red = accumulate != 0 || row.partial != 0;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int mo = 0; mo < K; ++mo)
-                if (ok[c]) {
-                    if (red) atomicAdd(yrow + po[c] + A * mo, alpha * acc[mo][c]);      // RED.ADD.F64
-                    else yrow[po[c] + A * mo] = alpha * acc[mo][c];
-                }
+        if (dbg) { t_main += c_1 - c_0; t_epi += clock64() - c_1; }
+    }
+    if (issuer) tma::bulk_wait_read0();                  // shared memory must outlive the last bulk read
+    if (dbg && lane == 0 && blockIdx.x < 1000) {         // per CTA: start, data ready, end (ns); smid; per-warp clocks summed
+        long long* o = dbg + (size_t)blockIdx.x * 8;
+        if (warp == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            o[0] = g_t0; o[1] = g_t1; o[4] = smid; o[7] = w0.w;
+        }
+        atomicMax(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)gtimer());
+        atomicAdd(reinterpret_cast<unsigned long long*>(o + 5), (unsigned long long)t_main);
+        atomicAdd(reinterpret_cast<unsigned long long*>(o + 6), (unsigned long long)t_epi);
+        atomicMax(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)t_main);
     }
 }
 

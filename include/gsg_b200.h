@@ -103,12 +103,17 @@ int gsg_plan_sync(gsg_plan* plan);
  * where a step is launch-latency bound), tiled above.  The environment variable GSG_FLAT sets the initial mode. */
 int gsg_plan_set_flat(gsg_plan* plan, int mode);
 /* CPU-side check of the row-tile kernel's tile program (no device needed) for pole class p of the library's own
- * H = periodic_DLF_matrix(k, n) and multi-cells of k^D doubles; budget_bytes = shared memory per tile, nrg = row
- * groups.  Two-call pattern: NULL outputs return counts_out = {tiles, rows, records}.  tiles_out: 48 int32 per tile
- * {nx, rec0, nrec, row0, rg_end[4], xq[40]}; rows_out: 4 int32 per row {q, rb, re, partial}; rec_h_out: k*k doubles
- * per record; rec_slot_out: the x slot of each record. */
+ * H = periodic_DLF_matrix(k, n) and multi-cells of k^D doubles; budget_bytes = shared memory of a CTA (barriers + 2 nrg
+ * staging cells + x cells + records), nrg = row groups.  Two-call pattern: NULL outputs return counts_out = {tiles,
+ * groups, blob bytes}.  tiles_out: 48 int32 per tile {nx, rec_ofs, rec_bytes, grp0, rg_end[4], xq[40]}; groups_out:
+ * 8 int32 per row group {q[4], rofs, nrec, partial mask, 0}; blob_out: the records, {int32 x-cell byte offset, int32
+ * row mask | arrival barrier << 8} followed by one k x k block (row-major doubles) per mask bit. */
 int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out,
-                              int32_t* rows_out, double* rec_h_out, int32_t* rec_slot_out, int64_t* counts_out);
+                              int32_t* groups_out, unsigned char* blob_out, int64_t* counts_out);
+/* CPU-side check of the row-tile kernel's lane order: nslots (a multiple of 32, >= PI) in-cell pole offsets
+ * a + k*A*b, dealt so that the 16 lanes of a half-warp fall into different 8-byte shared-memory banks; padding
+ * lanes are stored as ~offset. */
+int gsg_debug_rowtile_pole_order(int k, int A, int PI, int nslots, int32_t* out);
 /* human-readable summary: which kernel serves which pole classes in every direction ("kind(p, tiles)") */
 int gsg_plan_describe(const gsg_plan* plan, char* buf, size_t buflen);
 /* 1 if the operator applies of this plan currently take the flat kernel */

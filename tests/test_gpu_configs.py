@@ -326,7 +326,8 @@ def test_api_wrappers_wave_energy_mcerr(gsg, oracle):
 # ---------------------------------------------------------------------------------------------------------
 # multi-GPU driver inside the library (gsg_mg_*): virtual ranks on one device, and two processes over CUDA IPC
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("D,k,n,world", [(4, 3, 4, 2), (4, 3, 4, 4), (4, 3, 4, 8), (3, 3, 5, 4), (2, 3, 5, 2), (6, 3, 3, 8)])
+@pytest.mark.parametrize("D,k,n,world", [(4, 3, 4, 2), (4, 3, 4, 4), (4, 3, 4, 8), (3, 3, 5, 4), (2, 3, 5, 2), (6, 3, 3, 8),
+                                          (6, 3, 5, 4)])           # the last one has row-tile classes (p = 4, 5) in a partitioned plan
 def test_mg_virtual_ranks_match_single_gpu(gsg, oracle, cb, D, k, n, world):
     """`world` ranks of the in-library partitioned RK4 living in one process on one GPU (peer slabs = plain
     pointers, phases enqueued in lockstep): the owned parts reassemble to the oracle's RK4 state."""

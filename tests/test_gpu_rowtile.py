@@ -1,6 +1,7 @@
-"""GPU parity of the row-tile kernel for the long-pole classes (sweep_rowtile_kernel; GSG_ROWTILE=1): plans whose
-items have >= 64 poles, deep enough that several tile shapes occur (single-tile classes, subtree tiles with partial
-rows, recursion), against the C pole oracle.  Tolerance 1e-12 relative (BASELINE.json north_star)."""
+"""GPU parity of the row-tile kernel for the long-pole classes (sweep_rowtile_kernel, the default for plans whose
+items have >= 64 poles), deep enough that several tile shapes occur (single-tile classes, subtree tiles with partial
+rows, recursion), for 1 / 2 / 4 poles per lane, against the C pole oracle.  Tolerance 1e-12 relative (BASELINE.json
+north_star)."""
 import numpy as np
 import pytest
 
@@ -22,11 +23,14 @@ def cb():
     return cbaseline
 
 
-@pytest.mark.parametrize("D,k,n,budget", [(5, 3, 7, None), (6, 3, 5, None), (4, 4, 6, None), (5, 3, 6, 60), (6, 3, 6, 225)])
-def test_rowtile_every_axis_beta_and_gradient(gsg, oracle, cb, monkeypatch, D, k, n, budget):
+@pytest.mark.parametrize("D,k,n,budget,C", [(5, 3, 7, None, None), (6, 3, 5, None, None), (4, 4, 6, None, None), (5, 3, 6, 60, None),
+                                            (6, 3, 6, 112, 2), (6, 3, 6, 150, 1), (4, 5, 5, None, None)])
+def test_rowtile_every_axis_beta_and_gradient(gsg, oracle, cb, monkeypatch, D, k, n, budget, C):
     monkeypatch.setenv("GSG_ROWTILE", "1")
     if budget:
         monkeypatch.setenv("GSG_RT_BUDGET_KB", str(budget))
+    if C:
+        monkeypatch.setenv("GSG_RT_C", str(C))
     H = oracle.periodic_DLF_matrix(k, n)
     plan = gsg.Plan(D, k, n, "sparse", H=_scipy(H))
     plan.set_flat(0)

@@ -126,6 +126,8 @@ struct SweepClass {          // one launch of a sweep
     DevBuf<TileS2> s2tiles;     // second-generation streaming kernel
     DevBuf<RTWork> rtwork;      // row-tile kernel: (item, tile) work list, heaviest tiles first
     DevBuf<long long> rtsrc;    // ... and per work item the offsets in x of the tile's RT_MAXX cells
+    DevBuf<int> rtsched;        // ... and the persistent CTAs' item lists: sched[k * rtgrid + b] = k-th item of CTA b, -1 = end
+    int rtgrid = 0;
     DevBuf<int> rtzero;         // ... and the multi-cells that receive partial sums (zeroed before a beta = 0 sweep)
     bool stream2 = false;
     ShortParams sprm{};
@@ -313,17 +315,14 @@ int build_rowtile_program(gsg_plan& P) {
     size_t budget = SMEM_OPTIN_MAX - 1024;                // measured at D=6, k=3, n=8: one big tile per SM beats two of half the size
     if (const char* e = getenv("GSG_RT_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
     budget = std::min(budget, SMEM_OPTIN_MAX - 1024);
-    P.rt_C = (PI >= 192 && K <= 3) ? 4 : PI > 96 ? 2 : 1;
+    P.rt_C = (PI >= 192 && K <= 3) ? 4 : (PI > 96 && K <= 4) ? 2 : 1;       // k = 5 with two poles per lane spills
     if (const char* e = getenv("GSG_RT_C")) {
         const int c = atoi(e);
-        if (c == 1 || c == 2 || (c == 4 && K <= 3)) P.rt_C = c;
+        if (c == 1 || (c == 2 && K <= 4) || (c == 4 && K <= 3)) P.rt_C = c;
     }
     P.rt_PW = (PI + 32 * P.rt_C - 1) / (32 * P.rt_C);
     if (P.rt_PW > 8) return 0;
-    int nwarps = 8;
-    if (const char* e = getenv("GSG_RT_WARPS"))
-        if (atoi(e) == 16 && K <= 3 && P.rt_C <= 2) nwarps = 16;
-    P.rt_RG = std::max(1, std::min(RT_MAXRG, nwarps / P.rt_PW));
+    P.rt_RG = std::max(1, std::min(RT_MAXRG, 8 / P.rt_PW));
     if (rt_build_program(P.h_rowptr, P.h_col, P.h_val, P.KK2, K, (int)P.S.kDp, n, pmin, budget, P.rt_RG, P.rt_prog) != 0) {
         P.rt_prog = RTProgram();
         return 0;                                         // no tiling fits: the other kernels serve these classes
@@ -736,6 +735,26 @@ int build_direction(gsg_plan& P, int d /*0-based*/, Direction& dir, int exclude_
             }
             GSG_TRY(c.rtsrc.upload(src));
             GSG_TRY(c.rtwork.upload(work));
+            // persistent CTAs: the items (sorted by cost) are dealt to the least loaded CTA; cost = blocks + a fixed part
+            // (measured: ~1.6 us + 0.075 us per block of a tile)
+            static const int grid_env = getenv("GSG_RT_GRID") ? atoi(getenv("GSG_RT_GRID")) : -1;
+            const int G = grid_env == 0 ? c.ntiles : std::max(1, std::min(c.ntiles, grid_env > 0 ? grid_env : P.sm_count));
+            std::vector<std::vector<int>> mine(G);
+            std::vector<long long> load(G, 0);
+            for (size_t wi = 0; wi < work.size(); ++wi) {
+                int b = 0;
+                for (int h = 1; h < G; ++h)
+                    if (load[h] < load[b]) b = h;
+                mine[b].push_back((int)wi);
+                load[b] += P.rt_prog.tiles[work[wi].tile].rec_bytes / (K * K * 8) + 22;
+            }
+            size_t kmax = 0;
+            for (const auto& m : mine) kmax = std::max(kmax, m.size());
+            std::vector<int> sched((kmax + 1) * (size_t)G, -1);
+            for (int b = 0; b < G; ++b)
+                for (size_t k2 = 0; k2 < mine[b].size(); ++k2) sched[k2 * G + b] = mine[b][k2];
+            GSG_TRY(c.rtsched.upload(sched));
+            c.rtgrid = G;
             GSG_TRY(c.rtzero.upload(zero));
             dir.classes.push_back(std::move(c));
         }
@@ -1162,7 +1181,8 @@ int launch_short_tma(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         if (tn == 0) return 0;
         // one CTA per SM; a launch with little work (a rank's share of a partitioned plan) takes fewer CTAs, >= 12 tiles
         // each, so that the independent launches of a right-hand side run side by side instead of queueing for SMs
-        const int grid = std::max(1, std::min(pl.sm_count, std::min(tn, std::max(8, tn / 12))));
+        static const int sgrid_env = getenv("GSG_STREAM_GRID") ? atoi(getenv("GSG_STREAM_GRID")) : 0;   // SM split experiment
+        const int grid = std::max(1, std::min(sgrid_env > 0 ? sgrid_env : pl.sm_count, std::min(tn, std::max(8, tn / 12))));
         static_assert(sizeof(HDense<K>) + 256 < 32000, "dense blocks must fit the kernel parameter space");
         HDense<K> hd;
         const std::vector<double>& dense = pl.use_sq ? pl.dense_sq_host : pl.dense_host;     // Laplacian: pre-squared blocks
@@ -1203,7 +1223,8 @@ int launch_pair(gsg_plan& pl, cudaStream_t st, int j, const double* x, double* y
         auto kern = sweep_stream_kernel<K, true>;
         static thread_local size_t configured = 0;
         GSG_TRY(ensure_smem(kern, c.smem, configured));
-        const int grid = std::max(1, std::min(pl.sm_count, std::min(c.ntiles, std::max(8, c.ntiles / 12))));
+        static const int sgrid_env = getenv("GSG_STREAM_GRID") ? atoi(getenv("GSG_STREAM_GRID")) : 0;
+        const int grid = std::max(1, std::min(sgrid_env > 0 ? sgrid_env : pl.sm_count, std::min(c.ntiles, std::max(8, c.ntiles / 12))));
         HDense<K> hd;
         if ((int)pl.dense_host.size() != ShortDims<K>::htotal())
             return fail(GSG_ERR_UNSUPPORTED, "internal: dense block table size mismatch");
@@ -1334,20 +1355,15 @@ int launch_rowtile_k(gsg_plan& pl, cudaStream_t st, const Direction& dir, const 
         auto go = [&](auto kern) -> int {
             static thread_local size_t configured = 0;
             GSG_TRY(ensure_smem(kern, c.smem, configured));
-            kern<<<c.ntiles, threads, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.rt_offtab.p, c.rtwork.p,
-                                                     c.rtsrc.p, pl.rt_tiles.p, pl.rt_groups.p, pl.rt_recs.p, KDp, dir.A, pl.rt_PW,
-                                                     pl.rt_RG, pl.dbg);
+            // persistent: one CTA per SM walks its list of work items (GSG_RT_GRID=0 at plan creation: one CTA per item)
+            kern<<<c.rtgrid, threads, c.smem, st>>>(x, y, alpha, beta != 0.0 ? 1 : 0, dir.celltab.p, dir.rt_offtab.p, c.rtwork.p,
+                                                     c.rtsched.p, c.rtsrc.p, pl.rt_tiles.p, pl.rt_groups.p, pl.rt_recs.p, KDp, dir.A,
+                                                     pl.rt_PW, pl.rt_RG, pl.dbg);
             return 0;
         };
-        if (threads > 256) {                      // 16 warps (GSG_RT_WARPS=16): 128 registers per thread, C <= 2 at k <= 3
-            if constexpr (K <= 3) {
-                if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2, 512>));
-                else if (pl.rt_C == 1) GSG_TRY(go(sweep_rowtile_kernel<K, 1, 512>));
-                else return fail(GSG_ERR_UNSUPPORTED, "internal: 16-warp row-tile kernel needs C <= 2");
-            } else return fail(GSG_ERR_UNSUPPORTED, "internal: 16-warp row-tile kernel needs k <= 3");
-        }
-        else if (pl.rt_C == 4) { if constexpr (K <= 3) GSG_TRY(go(sweep_rowtile_kernel<K, 4, 256>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 4 for k > 3"); }
-        else if (pl.rt_C == 2) GSG_TRY(go(sweep_rowtile_kernel<K, 2, 256>));
+        if (threads > 256) return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile kernel launched with more than 8 warps");
+        if (pl.rt_C == 4) { if constexpr (K <= 3) GSG_TRY(go(sweep_rowtile_kernel<K, 4, 256>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 4 for k > 3"); }
+        else if (pl.rt_C == 2) { if constexpr (K <= 4) GSG_TRY(go(sweep_rowtile_kernel<K, 2, 256>)); else return fail(GSG_ERR_UNSUPPORTED, "internal: row-tile C = 2 for k > 4"); }
         else GSG_TRY(go(sweep_rowtile_kernel<K, 1, 256>));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return launch_check("sweep_rowtile", K, c);
@@ -1672,8 +1688,14 @@ struct PoolCtx {
 int sweep_scatter(gsg_plan& pl, PoolCtx& ctx, int d, double alpha, const double* x, double* y, bool reduced,
                   cudaEvent_t after, cudaEvent_t after2, std::vector<std::pair<const Direction*, const SweepClass*>>& deferred) {
     const Direction& dir = reduced ? pl.dirs_red[d] : pl.dirs[d];
+    // a row-tile launch that fills the machine (persistent, one CTA per SM) is an SM-filling kernel like the streaming
+    // one: queued with them, in order, instead of in front of them (GSG_RT_POOL=1: the high-priority pool as before)
+    static const bool rt_pool = getenv("GSG_RT_POOL") != nullptr;
     for (const SweepClass& c : dir.classes) {
-        if (c.kind == Kind::SHORT_TMA) { deferred.emplace_back(&dir, &c); continue; }
+        if (c.kind == Kind::SHORT_TMA || (c.kind == Kind::ROWTILE && !rt_pool && 2 * c.rtgrid >= pl.sm_count)) {
+            deferred.emplace_back(&dir, &c);
+            continue;
+        }
         cudaStream_t st;
         GSG_TRY(ctx.take(&st, after, after2));
         GSG_TRY(launch_class(pl, st, dir, c, x, y, alpha, 1.0));
@@ -1751,18 +1773,30 @@ int rhs_concurrent(gsg_plan& pl, const double* c, unsigned mask, const double* x
     static const bool one_stream_env = getenv("GSG_RHS_ONE_STREAM") != nullptr;
     // (event-timed launches stay on the main stream: a start event on a side stream would also time the wait for SMs)
     const bool one_stream = one_stream_env || (pl.prof_on && pl.prof_used < std::min(pl.prof_cap, pl.prof_ev.size()));
+    // order of the SM-filling launches: the row-tile launches of all directions, the PAIR launches, the streaming launches
+    // (GSG_RT_INTERLEAVE=1: direction by direction)
+    static const bool rt_interleave = getenv("GSG_RT_INTERLEAVE") != nullptr;
+    std::vector<size_t> dorder;
+    for (int pass = 0; pass < 2; ++pass)
+        for (size_t i = 0; i < deferred.size(); ++i) {
+            const bool is_rt = deferred[i].second->kind == Kind::ROWTILE;
+            if (rt_interleave ? pass == 0 : (pass == 0) == is_rt) dorder.push_back(i);
+        }
+    auto launch_deferred = [&](size_t i) -> int {
+        const int d = deferred_dir[i];
+        cudaStream_t st = pl.stream;
+        if (!one_stream) GSG_TRY(ctx.take_lo(&st, pl.ev_p1, pre_wait ? pre_wait[d] : nullptr));
+        else if (pre_wait && pre_wait[d]) GSG_CUDA(cudaStreamWaitEvent(pl.stream, pre_wait[d], 0));
+        return launch_class(pl, st, *deferred[i].first, *deferred[i].second, x, y, c[d], 1.0);
+    };
+    size_t di = 0;
+    for (; di < dorder.size() && !rt_interleave && deferred[dorder[di]].second->kind == Kind::ROWTILE; ++di) GSG_TRY(launch_deferred(dorder[di]));
     for (int j : pairs_todo) {
         cudaStream_t st = pl.stream;
         if (!one_stream) GSG_TRY(ctx.take_lo(&st, pl.ev_p1));
         GSG_TRY(do_pair(j, 1.0, st));
     }
-    for (size_t i = 0; i < deferred.size(); ++i) {
-        const int d = deferred_dir[i];
-        cudaStream_t st = pl.stream;
-        if (!one_stream) GSG_TRY(ctx.take_lo(&st, pl.ev_p1, pre_wait ? pre_wait[d] : nullptr));
-        else if (pre_wait && pre_wait[d]) GSG_CUDA(cudaStreamWaitEvent(pl.stream, pre_wait[d], 0));
-        GSG_TRY(launch_class(pl, st, *deferred[i].first, *deferred[i].second, x, y, c[d], 1.0));
-    }
+    for (; di < dorder.size(); ++di) GSG_TRY(launch_deferred(dorder[di]));
     return ctx.join();
 }
 
@@ -2251,9 +2285,7 @@ int gsg_debug_flat_tables(int D, int k, int n, int scheme, int d, int64_t* group
 
 // CPU-side check of the row-tile program (no device needed): the tile program of pole class p for the library's own
 // H = periodic_DLF_matrix(k, n), multi-cells of k^D doubles.  Two-call pattern: NULL outputs return the counts
-// {tiles, groups, blob bytes}.  tiles_out: (8 + 40) int32 per tile {nx, rec_ofs, rec_bytes, grp0, rg_end[4], xq[40]};
-// groups_out: 8 int32 per group {q[4], rofs, nrec, partial, 0}; blob_out: the record bytes ({int32 x cell byte offset,
-// int32 row mask} + one k x k block of doubles, row-major, per mask bit).
+// {tiles, groups, blob bytes}.  Layouts: include/gsg_b200.h.
 int gsg_debug_rowtile_program(int D, int k, int n, int p, int64_t budget_bytes, int nrg, int32_t* tiles_out, int32_t* groups_out,
                               unsigned char* blob_out, int64_t* counts_out) {
     GSG_TRY(check_dkn(D, k, n, 0));

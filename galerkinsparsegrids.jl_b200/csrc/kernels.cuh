@@ -1279,7 +1279,9 @@ sweep_consth_kernel(const double* __restrict__ X, double* __restrict__ Y, double
 // Warp (row group, pole warp) walks its ROW GROUPS: up to RT_R output rows that share most of their columns are
 // accumulated together, so an x value read from shared memory feeds up to RT_R * K DFMAs and a broadcast H value
 // feeds C: the loop is bound by the fp64 pipe, not by shared-memory wavefronts.  A record = {x cell, row mask}
-// followed by one K x K block per row of the mask (uniform branches).  Finished rows go through a per-row-group
+// followed by one K x K block per row of the mask (uniform branches); the blocks of rows (0, 1) and (2, 3) are
+// multiplied interleaved, which doubles the independent DFMA chains per thread (K * C -> 2 K C: with two warps per
+// scheduler the dependent-issue latency of DFMA is what bounds the loop).  Finished rows go through a per-row-group
 // staging cell in shared memory and leave as ONE bulk store (complete rows, beta = 0) or bulk reduce-add
 // (UBLKRED.ADD.F64: accumulating sweeps and the partial sums of rows above a subtree tile -- those rows are zeroed
 // beforehand when beta = 0), so y is written in whole 16-byte aligned multi-cells whatever the lane order.
@@ -1327,56 +1329,60 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-// shared memory: [RT_NBAR barriers (64 B)] [2 * RG staging cells] [nx x cells] [records]
+// shared memory: [RT_NBAR full barriers + 1 "x free" barrier (64 B)] [2 * RG staging cells] [nx x cells] [block entries]
+// PERSISTENT: CTA b takes the work items sched[b], sched[b + gridDim.x], ... until -1 (the host deals the items to
+// the CTAs, most expensive first onto the least loaded CTA).  Warp 0 doubles as
+// the producer: once every warp has left the main loops of a tile (the x cells and entries are dead -- the row
+// epilogues only touch registers and the staging cells), it issues the bulk copies of the CTA's next tile, so that
+// tile's load latency overlaps the epilogues of this one and no CTA launch sits between two tiles.
 template <int K, int C, int NT>
 __global__ void __launch_bounds__(NT, 1)
 sweep_rowtile_kernel(const double* __restrict__ X, double* __restrict__ Y, double alpha, int accumulate,
                      const CellOfs* __restrict__ celltab, const int* __restrict__ offtab,
-                     const RTWork* __restrict__ work, const long long* __restrict__ xsrc,
+                     const RTWork* __restrict__ work, const int* __restrict__ sched, const long long* __restrict__ xsrc,
                      const RTTile* __restrict__ tiles, const RTGroup* __restrict__ groups,
                      const unsigned char* __restrict__ recs, int KDp, int A, int PW, int RG,
-                     long long* __restrict__ dbg) {      // dbg: optional per-CTA time stamps (tools/stamps_rowtile.py)
+                     long long* __restrict__ dbg) {      // dbg: optional per-tile time stamps (tools/stamps_rowtile.py)
     constexpr int KK = K * K;
     extern __shared__ __align__(128) unsigned char smraw[];
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smraw);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smraw);     // [0, RT_NBAR): full; [RT_NBAR]: x free
     const unsigned cell_bytes = (unsigned)KDp * 8u;
-    const long long g_t0 = dbg ? gtimer() : 0;
-    long long t_main = 0, t_epi = 0;
     double* stage = reinterpret_cast<double*>(smraw + 64);                       // 2 * RG staging cells
     double* xs = reinterpret_cast<double*>(smraw + 64 + (size_t)2 * RG * cell_bytes);
+    const unsigned xs_s = tma::smem_u32(xs);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     int lane = tid & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));
-    // the only loads in front of the bulk copies: the work item and (independent of it) the source offsets of its cells
-    const int4 w0 = *reinterpret_cast<const int4*>(work + blockIdx.x);           // ctab, lo, hi, tile
-    const int4 w1 = *(reinterpret_cast<const int4*>(work + blockIdx.x) + 1);     // nx, rec_ofs, rec_bytes
-    const int nx = w1.x;
-    const unsigned rec_bytes = (unsigned)w1.z;
-    unsigned char* recs_s = reinterpret_cast<unsigned char*>(xs) + (size_t)nx * cell_bytes;
+    const int nwarps = PW * RG;
 
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < RT_NBAR; ++b) tma::mbar_init(tma::smem_u32(bar + b), 1);
+        tma::mbar_init(tma::smem_u32(bar + RT_NBAR), (unsigned)nwarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 2 * RG) stage[(size_t)tid * KDp + KDp - 1] = 0.0;        // the padding slot of a multi-cell stays zero
     __syncthreads();
-    if (warp == 0) {
-        // cell i arrives on barrier (i * RT_NBAR) / nx, the records on barrier 0
+
+    // producer (whole warp 0): the bulk copies of work item wi; cell i arrives on barrier (i * RT_NBAR) / nx, the
+    // entries on barrier 0.  The only loads in front of the copies: the work item and its cells' source offsets.
+    auto issue_tile = [&](int wi) {
+        const int4 v1 = *(reinterpret_cast<const int4*>(work + wi) + 1);          // nx, rec_ofs, rec_bytes
+        const int nx = v1.x;
         if (lane < RT_NBAR) {
             const int c0 = (lane * nx + RT_NBAR - 1) / RT_NBAR, c1 = ((lane + 1) * nx + RT_NBAR - 1) / RT_NBAR;
-            tma::mbar_expect_tx(tma::smem_u32(bar + lane), (unsigned)(c1 - c0) * cell_bytes + (lane == 0 ? rec_bytes : 0u));
+            tma::mbar_expect_tx(tma::smem_u32(bar + lane), (unsigned)(c1 - c0) * cell_bytes + (lane == 0 ? (unsigned)v1.z : 0u));
         }
         __syncwarp();
-        if (lane == 0) tma::bulk_g2s(tma::smem_u32(recs_s), recs + w1.y, rec_bytes, tma::smem_u32(bar));
+        if (lane == 0) tma::bulk_g2s(xs_s + (unsigned)nx * cell_bytes, recs + v1.y, (unsigned)v1.z, tma::smem_u32(bar));
         for (int i = lane; i < nx; i += 32)
-            tma::bulk_g2s(tma::smem_u32(xs + (size_t)i * KDp), X + xsrc[(size_t)blockIdx.x * RT_MAXX + i], cell_bytes,
+            tma::bulk_g2s(xs_s + (unsigned)i * cell_bytes, X + xsrc[(size_t)wi * RT_MAXX + i], cell_bytes,
                           tma::smem_u32(bar + (i * RT_NBAR) / nx));
-    }
-    const RTTile* __restrict__ T = tiles + w0.w;
-    const CellOfs* __restrict__ ctab = celltab + w0.x;
-    const long long item_ofs = (long long)KDp * w0.y;
+    };
+    int wi = sched[blockIdx.x];
+    if (warp == 0 && wi >= 0) issue_tile(wi);
+
     // per-lane pole constants: pole slot c of this lane = entry (pw * C + c) * 32 + lane of the bank-permuted table;
     // a negative entry ~o marks a padding lane (it reads pole offset o like a neighbour and stores nothing)
     const int pw = warp % PW, rg = warp / PW;
@@ -1389,111 +1395,179 @@ sweep_rowtile_kernel(const double* __restrict__ X, double* __restrict__ Y, doubl
         pob[c] = (unsigned)(v >= 0 ? v : ~v) * 8u;
     }
     const unsigned A8 = (unsigned)A * 8u;
-    const int g_begin = T->grp0 + (rg == 0 ? 0 : T->rg_end[rg - 1]), g_end = T->grp0 + T->rg_end[rg];
-    const unsigned xs_s = tma::smem_u32(xs), rs_s = tma::smem_u32(recs_s);
     const unsigned st_s = tma::smem_u32(stage) + (unsigned)(2 * rg) * cell_bytes;
     const bool issuer = pw == 0 && lane == 0;
     const int nbar = 32 * PW;
-    if (g_begin >= g_end) return;
-    int4 gq = *reinterpret_cast<const int4*>(groups + g_begin);
-    int4 gm = *(reinterpret_cast<const int4*>(groups + g_begin) + 1);             // rofs, nrec, partial, pad
-    tma::mbar_wait(tma::smem_u32(bar), 0);
-    const long long g_t1 = dbg ? gtimer() : 0;
-    unsigned arrived = 1u;                  // barriers this warp has seen complete
     unsigned sbuf = 0;                      // staging cell of the next row (alternates)
 
-    for (int gi = g_begin; gi < g_end; ++gi) {
-        const int4 cq = gq, cm = gm;
-        if (gi + 1 < g_end) {               // next group's descriptor while this one is computed
-            gq = *reinterpret_cast<const int4*>(groups + gi + 1);
-            gm = *(reinterpret_cast<const int4*>(groups + gi + 1) + 1);
-        }
-        const int qs[RT_R] = {cq.x, cq.y, cq.z, cq.w};
-        long long yofs[RT_R];               // output cells, fetched now and used in the epilogue
-#pragma unroll
-        for (int r = 0; r < RT_R; ++r) {
-            yofs[r] = 0;
-            if (issuer && qs[r] >= 0) {
-                const CellOfs co = ctab[qs[r]];
-                yofs[r] = co.bq + item_ofs + co.kc * w0.z;
+    for (int it = 0; wi >= 0; ++it) {
+        const int wcur = wi;
+        wi = sched[(size_t)(it + 1) * gridDim.x + blockIdx.x];        // -1 after the CTA's last item
+        const int wnext = wi;
+        const unsigned par = (unsigned)it & 1u;
+        const long long g_t0 = dbg ? gtimer() : 0;
+        long long t_main = 0, t_epi = 0;
+        const int4 w0 = *reinterpret_cast<const int4*>(work + wcur);              // ctab, lo, hi, tile
+        const int4 w1 = *(reinterpret_cast<const int4*>(work + wcur) + 1);        // nx, rec_ofs, rec_bytes
+        const unsigned rs_s = xs_s + (unsigned)w1.x * cell_bytes;
+        const RTTile* __restrict__ T = tiles + w0.w;
+        const CellOfs* __restrict__ ctab = celltab + w0.x;
+        const long long item_ofs = (long long)KDp * w0.y;
+        const int g_begin = T->grp0 + (rg == 0 ? 0 : T->rg_end[rg - 1]), g_end = T->grp0 + T->rg_end[rg];
+        // a warp leaves the tile's x cells and entries behind; warp 0 then fetches the CTA's next tile
+        auto done_reading = [&]() {
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(tma::smem_u32(bar + RT_NBAR));
+            if (warp == 0 && wnext >= 0) {
+                tma::mbar_wait(tma::smem_u32(bar + RT_NBAR), par);
+                issue_tile(wnext);
             }
+        };
+        int4 gq = make_int4(-1, -1, -1, -1), gm = make_int4(0, 0, 0, 0);
+        if (g_begin < g_end) {
+            gq = *reinterpret_cast<const int4*>(groups + g_begin);
+            gm = *(reinterpret_cast<const int4*>(groups + g_begin) + 1);          // rofs, nrec, partial, pad
         }
-        double acc[RT_R][K][C];
-#pragma unroll
-        for (int r = 0; r < RT_R; ++r)
-#pragma unroll
-            for (int m = 0; m < K; ++m)
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[r][m][c] = 0.0;
-        unsigned ptr = rs_s + (unsigned)cm.x;
-        const long long c_0 = dbg ? clock64() : 0;
-        for (int i = 0; i < cm.y; ++i) {
-            const int2 hd = lds_v2s32(ptr);          // x cell offset (bytes); row mask | barrier of the cell << 8
-            ptr += 8;
-            const unsigned bi = ((unsigned)hd.y >> 8) & (RT_NBAR - 1);
-            if (!((arrived >> bi) & 1u)) {           // uniform over the warp
-                tma::mbar_wait(tma::smem_u32(bar + bi), 0);
-                arrived |= 1u << bi;
+        // EVERY warp waits for the tile's first barrier before it may signal "done reading": a warp without rows in
+        // this tile must not run ahead and arrive twice in one phase of the "x free" barrier
+        tma::mbar_wait(tma::smem_u32(bar), par);
+        if (g_begin >= g_end) {             // no rows for this row group in this tile
+            done_reading();
+            continue;
+        }
+        const long long g_t1 = dbg ? gtimer() : 0;
+        unsigned arrived = 1u;              // barriers this warp has seen complete in this tile
+
+        for (int gi = g_begin; gi < g_end; ++gi) {
+            const int4 cq = gq, cm = gm;
+            if (gi + 1 < g_end) {           // next group's descriptor while this one is computed
+                gq = *reinterpret_cast<const int4*>(groups + gi + 1);
+                gm = *(reinterpret_cast<const int4*>(groups + gi + 1) + 1);
             }
-            const unsigned xa = xs_s + (unsigned)hd.x;
-            double xv[K][C];
-#pragma unroll
-            for (int mi = 0; mi < K; ++mi)
-#pragma unroll
-                for (int c = 0; c < C; ++c) xv[mi][c] = lds_f64(xa + pob[c] + A8 * mi);
+            const int qs[RT_R] = {cq.x, cq.y, cq.z, cq.w};
+            long long yofs[RT_R];           // output cells, fetched now and used in the epilogue
 #pragma unroll
             for (int r = 0; r < RT_R; ++r) {
-                if (hd.y & (1 << r)) {               // uniform over the CTA's lanes
-                    double h[KK];
-#pragma unroll
-                    for (int e = 0; e < KK; ++e) h[e] = lds_f64(ptr + e * 8);
-                    ptr += KK * 8;
-#pragma unroll
-                    for (int mi = 0; mi < K; ++mi)
-#pragma unroll
-                        for (int mo = 0; mo < K; ++mo)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) acc[r][mo][c] = fma(h[mo * K + mi], xv[mi][c], acc[r][mo][c]);
+                yofs[r] = 0;
+                if (issuer && qs[r] >= 0) {
+                    const CellOfs co = ctab[qs[r]];
+                    yofs[r] = co.bq + item_ofs + co.kc * w0.z;
                 }
             }
-        }
-        const long long c_1 = dbg ? clock64() : 0;
+            double acc[RT_R][K][C];
 #pragma unroll
-        for (int r = 0; r < RT_R; ++r) {
-            if (qs[r] < 0) continue;
-            const unsigned sb = st_s + sbuf * cell_bytes;
-            if (issuer) bulk_wait_read1();               // the bulk operation issued from this staging cell two rows ago has read it
-            named_bar_sync(1 + rg, nbar);
+            for (int r = 0; r < RT_R; ++r)
 #pragma unroll
-            for (int c = 0; c < C; ++c)
+                for (int m = 0; m < K; ++m)
 #pragma unroll
-                for (int mo = 0; mo < K; ++mo)
-                    if (ok[c]) sts_f64(sb + pob[c] + A8 * mo, alpha * acc[r][mo][c]);
-            tma::fence_proxy_async();
-            named_bar_sync(1 + rg, nbar);
-            if (issuer) {
-                double* yrow = Y + yofs[r];
-                if (accumulate != 0 || ((cm.z >> r) & 1)) tma::bulk_red_add_f64(yrow, sb, cell_bytes);
-                else tma::bulk_s2g(yrow, sb, cell_bytes);
-                tma::bulk_commit();
+                    for (int c = 0; c < C; ++c) acc[r][m][c] = 0.0;
+            const long long c_0 = dbg ? clock64() : 0;
+            unsigned ptr = rs_s + (unsigned)cm.x;
+            int2 hd = lds_v2s32(ptr);                // x cell offset (bytes); row mask | barrier of the cell << 8
+            for (int i = 0; i < cm.y; ++i) {
+                const int2 hc = hd;
+                const unsigned bi = ((unsigned)hc.y >> 8) & (RT_NBAR - 1);
+                if (!((arrived >> bi) & 1u)) {       // uniform over the warp
+                    tma::mbar_wait(tma::smem_u32(bar + bi), par);
+                    arrived |= 1u << bi;
+                }
+                const unsigned xa = xs_s + (unsigned)hc.x;
+                double xv[K][C];
+#pragma unroll
+                for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xv[mi][c] = lds_f64(xa + pob[c] + A8 * mi);
+                unsigned bp = ptr + 8;
+                ptr += 8 + KK * 8 * __popc(hc.y & ((1 << RT_R) - 1));
+                if (i + 1 < cm.y) hd = lds_v2s32(ptr);         // the next record's header while this one is multiplied
+#pragma unroll
+                for (int half = 0; half < RT_R / 2; ++half) {
+                    const int m2 = (hc.y >> (2 * half)) & 3; // uniform over the CTA's lanes
+                    if (m2 == 3) {                   // both rows of the pair: 2 K C independent DFMA chains
+                        double ha[KK], hb[KK];
+#pragma unroll
+                        for (int e = 0; e < KK; ++e) ha[e] = lds_f64(bp + e * 8);
+#pragma unroll
+                        for (int e = 0; e < KK; ++e) hb[e] = lds_f64(bp + (KK + e) * 8);
+                        bp += 2 * KK * 8;
+#pragma unroll
+                        for (int mi = 0; mi < K; ++mi) {
+#pragma unroll
+                            for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                                for (int c = 0; c < C; ++c)
+                                    acc[2 * half][mo][c] = fma(ha[mo * K + mi], xv[mi][c], acc[2 * half][mo][c]);
+#pragma unroll
+                            for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                                for (int c = 0; c < C; ++c)
+                                    acc[2 * half + 1][mo][c] = fma(hb[mo * K + mi], xv[mi][c], acc[2 * half + 1][mo][c]);
+                        }
+                    } else if (m2 != 0) {
+                        double ha[KK];
+#pragma unroll
+                        for (int e = 0; e < KK; ++e) ha[e] = lds_f64(bp + e * 8);
+                        bp += KK * 8;
+                        if (m2 == 1) {
+#pragma unroll
+                            for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                                for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                                    for (int c = 0; c < C; ++c)
+                                        acc[2 * half][mo][c] = fma(ha[mo * K + mi], xv[mi][c], acc[2 * half][mo][c]);
+                        } else {
+#pragma unroll
+                            for (int mi = 0; mi < K; ++mi)
+#pragma unroll
+                                for (int mo = 0; mo < K; ++mo)
+#pragma unroll
+                                    for (int c = 0; c < C; ++c)
+                                        acc[2 * half + 1][mo][c] = fma(ha[mo * K + mi], xv[mi][c], acc[2 * half + 1][mo][c]);
+                        }
+                    }
+                }
             }
-            sbuf ^= 1u;
+            if (gi + 1 == g_end) done_reading();
+            const long long c_1 = dbg ? clock64() : 0;
+#pragma unroll
+            for (int r = 0; r < RT_R; ++r) {
+                if (qs[r] < 0) continue;
+                // two staging cells alternate; ONE barrier per row tells the row group's warps both "this row is staged"
+                // and "the other cell is free again" (the issuer first waits for the previous row's bulk read)
+                const unsigned sb = st_s + sbuf * cell_bytes;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int mo = 0; mo < K; ++mo)
+                        if (ok[c]) sts_f64(sb + pob[c] + A8 * mo, alpha * acc[r][mo][c]);
+                tma::fence_proxy_async();
+                if (issuer) tma::bulk_wait_read0();
+                named_bar_sync(1 + rg, nbar);
+                if (issuer) {
+                    double* yrow = Y + yofs[r];
+                    if (accumulate != 0 || ((cm.z >> r) & 1)) tma::bulk_red_add_f64(yrow, sb, cell_bytes);
+                    else tma::bulk_s2g(yrow, sb, cell_bytes);
+                    tma::bulk_commit();
+                }
+                sbuf ^= 1u;
+            }
+            if (dbg) { t_main += c_1 - c_0; t_epi += clock64() - c_1; }
         }
-        if (dbg) { t_main += c_1 - c_0; t_epi += clock64() - c_1; }
+        if (dbg && lane == 0 && wcur < 1000) {       // per tile: start, data ready, end (ns); smid; per-warp clocks summed
+            long long* o = dbg + (size_t)wcur * 8;
+            if (warp == 0) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                o[0] = g_t0; o[1] = g_t1; o[4] = smid; o[7] = w0.w;
+            }
+            atomicMax(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)gtimer());
+            atomicAdd(reinterpret_cast<unsigned long long*>(o + 5), (unsigned long long)t_main);
+            atomicAdd(reinterpret_cast<unsigned long long*>(o + 6), (unsigned long long)t_epi);
+            atomicMax(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)t_main);
+        }
     }
     if (issuer) tma::bulk_wait_read0();                  // shared memory must outlive the last bulk read
-    if (dbg && lane == 0 && blockIdx.x < 1000) {         // per CTA: start, data ready, end (ns); smid; per-warp clocks summed
-        long long* o = dbg + (size_t)blockIdx.x * 8;
-        if (warp == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            o[0] = g_t0; o[1] = g_t1; o[4] = smid; o[7] = w0.w;
-        }
-        atomicMax(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)gtimer());
-        atomicAdd(reinterpret_cast<unsigned long long*>(o + 5), (unsigned long long)t_main);
-        atomicAdd(reinterpret_cast<unsigned long long*>(o + 6), (unsigned long long)t_epi);
-        atomicMax(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)t_main);
-    }
 }
 
 // development aid: a spinner with a chosen resource footprint, to probe which kernels share an SM

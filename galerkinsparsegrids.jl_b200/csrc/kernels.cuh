@@ -619,8 +619,10 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             tma::mbar_init(tma::smem_u32(&bars[s]), 32);      // every loader lane writes descriptor words and arrives
-            tma::mbar_init(tma::smem_u32(&bars[4 + s]), StreamCfg<PAIR>::CW);
-            tma::mbar_init(tma::smem_u32(&bars[8 + s]), 1);
+            // "computed" and "free": every lane arrives for itself (under the PTX model lane 0's arrive after a
+            // __syncwarp would do, but compute-sanitizer's racecheck credits only a thread's own arrive)
+            tma::mbar_init(tma::smem_u32(&bars[4 + s]), 32 * StreamCfg<PAIR>::CW);
+            tma::mbar_init(tma::smem_u32(&bars[8 + s]), 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -697,7 +699,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
             if (it >= 1) {
                 bulk_wait_read1();                  // the previous tile's stage has been read out
                 __syncwarp();
-                if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[8 + (it - 1) % NS]));
+                tma::mbar_arrive(tma::smem_u32(&bars[8 + (it - 1) % NS]));
             }
             if (dbg && blockIdx.x == 0 && it < 64 && lane == 0) {
                 dbg[it * 8 + 3] = c0; dbg[it * 8 + 4] = c1; dbg[it * 8 + 5] = clock64();
@@ -718,8 +720,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
             const long long w1 = clock64();
             const int P = sdesc[s].P, nr = sdesc[s].nr;
             if (P < 0) {
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));      // pass the end marker on
+                tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));      // pass the end marker on
                 break;
             }
             double* xs = ring + (size_t)s * prm.stage_doubles;
@@ -737,8 +738,7 @@ sweep_stream_kernel(const double* __restrict__ X, double* __restrict__ Y, double
                 case 3: if constexpr (ShortDims<K>::pmax() >= 3) short_tile_compute2<K, 3, 1>(xs, hd, nr, KDp, prm.A, PI, pole_off, alpha, ctid, ncth); break;
             }
             tma::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));
+            tma::mbar_arrive(tma::smem_u32(&bars[4 + s]));
             if (dbg && blockIdx.x == 0 && it < 64 && ctid == 0) {
                 dbg[it * 8 + 6] = w1 - w0; dbg[it * 8 + 7] = clock64() - w1;
             }

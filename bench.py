@@ -446,7 +446,8 @@ def main():
     # CUDA events around the dominant kernel for a bounded sample of the timed region's launches (the first
     # 72 = two steps' worth: timing all of them costs ~8 % of the step, this sample ~0.5 %)
     # (the in-library multi-GPU driver replays the step from a CUDA graph: its sample is taken after the timed region)
-    plan.profile_enable(0 if (os.environ.get("GSG_NO_PROFILE_EVENTS") or mg is not None) else 72)
+    # (the flat path of the small configurations replays its steps from a CUDA graph as well: no event sample there)
+    plan.profile_enable(0 if (os.environ.get("GSG_NO_PROFILE_EVENTS") or mg is not None or plan.flat_active) else 72)
     l0 = g.launch_count()
     sampler.start()
     barrier()
@@ -471,6 +472,12 @@ def main():
         plan.profile_enable(72)
         mg.step(a, DT, 2)                       # eager (not replayed) steps with events around the dominant kernel
         mg.sync()
+        barrier()
+    if mg is None and plan.flat_active and not os.environ.get("GSG_NO_PROFILE_EVENTS"):
+        barrier()
+        plan.profile_enable(8)
+        run(2)                                  # eager (not replayed) steps with events around the flat launches
+        torch.cuda.synchronize(device)
         barrier()
     n_prof, prof_ms, prof_dofs = plan.profile_read()
     plan.profile_enable(False)

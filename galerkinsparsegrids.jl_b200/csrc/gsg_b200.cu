@@ -1878,7 +1878,10 @@ int run_steps(gsg_plan& pl, int64_t nsteps, Step one_step) {
     // Opt-in (GSG_GRAPH=1): measured SLOWER at D=6 (6.2 vs 5.4 ms per step) -- inside a graph the
     // independent kernel nodes of a sweep lose their launch order and stream priorities, the persistent
     // streaming kernel takes every SM first and the long-pole kernels run after it instead of beside it.
-    const bool use_graph = nsteps >= 3 && !pl.prof_on && !pl.dbg && getenv("GSG_GRAPH") != nullptr;
+    // The flat path (small index sets: a step is 5 launches of a few microseconds each) is launch-latency bound and has
+    // no stream fork/join inside a step: there the replay is the default (GSG_NO_GRAPH=1 turns it off).
+    static const bool graph_env = getenv("GSG_GRAPH") != nullptr, no_graph_env = getenv("GSG_NO_GRAPH") != nullptr;
+    const bool use_graph = nsteps >= 3 && !pl.prof_on && !pl.dbg && (graph_env || (flat_on(pl) && !no_graph_env));
     if (!use_graph) {
         for (int64_t s = 0; s < nsteps; ++s) GSG_TRY(one_step());
         return 0;

@@ -17,8 +17,10 @@
 // Kernels in this file, by pole length N' = K * 2^p of the class they serve:
 //   sweep_stream_kernel<K, PAIR>   N' <= 32   persistent TMA ring (loader / storer / compute warps); PAIR = one
 //                                             pass for both directions of a pair over 2-D sub-planes (n' <= 2)
-//   sweep_consth_kernel<K, P>      N' = 48    matrix unrolled into constant-bank operands (structural pattern)
-//   sweep_long2_kernel<K, C, NB>   N' >= 96   register-tiled: lanes = poles, C poles per lane, record stream
+//   sweep_rowtile_kernel<K, C>     N' >= 48   (items with >= 64 poles) persistent; whole multi-cells by TMA, row groups,
+//                                             bank-permuted lanes = poles, staged bulk store / reduce-add output
+//   sweep_consth_kernel<K, P>      N' = 48    (smaller items) matrix unrolled into constant-bank operands
+//   sweep_long2_kernel<K, C, NB>   N' >= 96   (smaller items) register-tiled: lanes = poles, C poles per lane, record stream
 //   sweep_short_tma_kernel (small k^D: many multi-cells per tile), sweep_generic_kernel (any k <= 10, any length)
 //   rk_stage_kernel, rk_final_kernel, rk4_taylor_kernel(_cells)   RK4 updates
 //   sweep_flat_kernel<K>           small index sets: one launch per right-hand side, all directions, no atomics

@@ -31,6 +31,7 @@ CONFIGS = {
     "d4k3n7": (4, 3, 7),     # config 3 operator (latency regime)
     "d2k3n8": (2, 3, 8),     # config 2 operator (latency regime)
     "recon": (4, 4, 8),      # config 5: reconstruct_DG of a D=4 sparse k=4 n=8 interpolant (points/s)
+    "wave2d": (2, 3, 8),     # config 2 as the reference runs it: wave equation [u; v]' = [v; lap u], classical RK4
 }
 FP64_PEAK_TFLOPS = 37.0      # nominal B200 fp64 (MEASURED_PEAKS.json holds only the copy bandwidth and the bf16 GEMM)
 DT = 1.0e-4                  # stable for RK4 at D=6, n=8 (dt_max ~ 2.2e-4)
@@ -249,6 +250,60 @@ def workload_name(D, k, n, N):
             f"(BASELINE config {4 if (D, k, n) == (6, 3, 8) else '-'})")
 
 
+def run_wave(args, rank, local_rank, world):
+    """--config wave2d: the 2-D wave evolution of BASELINE config 2 (src/pdes.jl:54-68 with order = "4"): one step =
+    one classical RK4 step of [u; v]' = [v; laplacian u] through gsg_rk4_wave_dev (the Laplacian takes the pre-squared
+    blocks S_p = (H[:N',:N'])^2, one sweep per direction, src/multidim_derivative.jl:71-79).  Replicas at N > 1."""
+    import numpy as np
+    import torch
+
+    import gsg_b200 as g
+    D, k, n = CONFIGS["wave2d"]
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    W, K = max(args.warmup, 3), args.steps
+    plan = g.Plan(D, k, n, device=local_rank)
+    N = plan.size
+    v1d = g.vcoeffs_DG(1, k, n, lambda x: math.sin(2 * math.pi * x))
+    u0 = g.tensor_construct(D, k, n, [v1d] * D)
+    stream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(stream)
+    plan.set_stream(stream)
+    u = plan.tensor_construct_dev([v1d] * D, device=device)
+    v = torch.zeros_like(u)
+    plan.rk4_wave_dev(u, v, DT, W)
+    torch.cuda.synchronize(device)
+    l0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    plan.rk4_wave_dev(u, v, DT, K)
+    e1.record(stream)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    launches = g.launch_count() - l0
+    hu, hv = torch.from_numpy(u0.copy()).pin_memory(), torch.zeros(N, dtype=torch.float64).pin_memory()
+    plan.rk4_wave(hu.numpy(), hv.numpy(), DT, 1)                 # warm the host-buffer path
+    t0 = time.perf_counter()
+    rc = g.lib.gsg_rk4_wave(plan._h, g._ptr(hu.numpy()), g._ptr(hv.numpy()), DT, K)
+    t1 = time.perf_counter()
+    if rc != 0:
+        raise SystemExit("gsg_rk4_wave failed")
+    energy = plan.energy(hu.numpy(), hv.numpy())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "RK4 DOF-updates/sec, 2-D wave (D=%d sparse, k=%d, n=%d)" % (D, k, n), "value": 2 * N * K / (ms * 1e-3),
+            "unit": "DOF-updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"2-D wave equation on the sparse grid, k={k} n={n}, state [u; v] = 2 x {N} DOFs, classical RK4 "
+                                   "(BASELINE config 2 with order 4), u0 = sin(2 pi x) sin(2 pi y), v0 = 0", "dt": DT,
+                       "sweep_path": "flat kernel, pre-squared Laplacian blocks" if plan.flat_active else "tiled class kernels"},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": 2 * N * K / (t1 - t0), "unit": "DOF-updates/s", "h2d_bytes_per_step": 16.0 * N / K,
+                    "d2h_bytes_per_step": 16.0 * N / K, "call": f"gsg_rk4_wave(plan, u_host, v_host, dt, nsteps={K})"},
+            "gpu_launches": launches, "energy_sqrt": math.sqrt(max(energy, 0.0)),
+        }), flush=True)
+
+
 def run_recon(args, rank, local_rank, world):
     """--config recon: batched reconstruct_DG (BASELINE config 5).  One step = one batch of `npts` uniform points
     (counter-based generator, seed 20240); points are sharded over the ranks, coefficients replicated."""
@@ -370,6 +425,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.config == "wave2d":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the RK4 advection path; --config wave2d is a GPU-only line"}))
+            return
+        run_wave(args, rank, local_rank, world)
+        return
     if args.config == "recon":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the RK4 path; --config recon carries its own cpu_baseline"}))

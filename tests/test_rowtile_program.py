@@ -116,3 +116,34 @@ def test_rowtile_pole_order_is_a_conflict_free_permutation(gsg, k, D, C, PW):
         assert extra == forced, (d, extra, forced)
         if k == 3:
             assert forced <= 8      # A = 27 at D = 6: the banks (a + b) mod 16 hold 13 .. 18 poles for 16 half-warps
+
+
+def _plan_shape(k, D):
+    """poles per lane / pole warps / row groups as build_rowtile_program chooses them (csrc/gsg_b200.cu)"""
+    PI = k ** (D - 1)
+    C = 4 if (PI >= 192 and k <= 3) else 2 if (PI > 96 and k <= 4) else 1
+    PW = (PI + 32 * C - 1) // (32 * C)
+    return PI, C, PW, max(1, min(4, 8 // PW))
+
+
+@pytest.mark.parametrize("k,D", [(2, 7), (2, 8), (2, 9), (2, 10), (3, 5), (3, 6), (4, 4), (4, 5), (5, 4)])
+def test_rowtile_program_every_plan_shape(gsg, k, D):
+    """every (k, D) whose plans take the row-tile kernel (k <= 5, 64 <= k^(D-1) <= 512), default shared-memory budget,
+    every long class up to n = 7 (n <= 10 was swept once by hand): the program reproduces H_p x and fits"""
+    PI, C, PW, RG = _plan_shape(k, D)
+    assert 64 <= PI <= 512 and PW <= 8
+    pmin = 0
+    while (k << pmin) <= 32 and pmin <= 3:            # first class the streaming kernel does not serve
+        pmin += 1
+    n = 7
+    H = gsg.periodic_DLF_matrix(k, n).toarray()
+    KDp = (k ** D + 1) & ~1
+    for p in range(pmin, n + 1):
+        prog = gsg.rowtile_program(D, k, n, p, 226 * 1024, RG)
+        Np = k << p
+        x = np.random.default_rng(p).standard_normal(Np)
+        y, complete, partial, _ = _replay(prog, k, p, x, KDp)
+        ref = H[:Np, :Np] @ x
+        assert np.linalg.norm(y - ref) <= 1e-13 * np.linalg.norm(ref), (k, D, p)
+        assert np.all((complete == 1) & (partial == 0) | (complete == 0) & (partial >= 1))
+        assert max(64 + (2 * RG + int(T[0])) * KDp * 8 + int(T[2]) for T in prog["tiles"]) <= 226 * 1024

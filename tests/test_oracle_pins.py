@@ -137,6 +137,28 @@ def test_reconstruction_1d_bound(oracle, k, l):
     assert err < 1.0 / (1 << (l + k - 1))
 
 
+@pytest.mark.parametrize("k,l", [(1, 4), (2, 3), (2, 6), (3, 5), (4, 3), (5, 2), (5, 4)])
+def test_reconstruction_2d_sparse_bound(oracle, k, l):
+    """test/hier_DG.jl:59-67: L2 error^2 of the SPARSE 2-D reconstruction of sin(4x + y) < 2^-(l+k-2).  The projection of
+    a product function onto the tensor basis is the product of the 1-D projections, so the coefficients are
+    tensor_construct(sin 4x, cos y) + tensor_construct(cos 4x, sin y) (the reference integrates the 2-D closure with
+    HCubature); the error integral is a tensor Gauss-Legendre rule on the finest cells through the batched reconstruct."""
+    D = 2
+    c1 = {name: oracle.coeffs_1d(k, l, f) for name, f in
+          [("s4", lambda x: math.sin(4 * x)), ("c4", lambda x: math.cos(4 * x)), ("s", math.sin), ("c", math.cos)]}
+    vect = oracle.tensor_construct(D, k, l, [c1["s4"], c1["c"]]) + oracle.tensor_construct(D, k, l, [c1["c4"], c1["s"]])
+    nc = 1 << l
+    gx, gw = np.polynomial.legendre.leggauss(8)
+    xs = np.concatenate([(c + 0.5 + 0.5 * gx) / nc for c in range(nc)])
+    ws = np.concatenate([0.5 * gw / nc for _ in range(nc)])
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    W = np.outer(ws, ws)
+    vals = oracle.reconstruct_DG_batch(D, k, l, vect, np.stack([X.ravel(), Y.ravel()], axis=1))
+    err = float(np.sum(W.ravel() * (vals - np.sin(4 * X.ravel() + Y.ravel())) ** 2))
+    print(f"2-D sparse reconstruction k={k} l={l}: L2 error^2 {err:.3e} < {1.0 / (1 << (l + k - 2)):.3e}")
+    assert err < 1.0 / (1 << (l + k - 2))
+
+
 def test_wave_energy_2d_sparse(oracle):
     """test/solvers.jl:54-77 (2-D sparse, k=3): sqrt(E) ~ sqrt(2) pi, energy non-increasing and
     conserved to 1e-8 -- here with fixed-step RK4 at n=4 instead of ODE.jl's adaptive ode45/78."""
